@@ -1,0 +1,265 @@
+// bch_kernel.cu -- binary BCH decoder over GF(2^m) for the DVB-S2 outer code on sm_100a.
+//
+// Behavioural contract (bit-exact outputs and return codes):
+//   lib/bch.cc:467-487  decode(u8): copy systematic bytes, syndrome, Berlekamp, roots, flips
+//   lib/bch.cc:216-222,175-189  syndromes S_i = r(alpha^i), i = 1..2t (all-zero -> return 0)
+//   lib/bch.cc:224-304  simplified Berlekamp, Lin & Costello table form (rows mu = -1/2, 0..t)
+//   lib/bch.cc:306-385 + lib/gf.cc:289-404  roots over exponents s+1 .. n+s
+//   lib/bch.cc:428-452  flips of message bits only, network bit order
+//
+// Design: one warp per codeword.  Syndromes are evaluated directly as r(alpha^i) (the reference
+// first reduces r mod g with a serial byte LUT; same field element) with the 32 lanes striding
+// over the bytes, odd i only (S_2i = S_i^2 in a binary code).  Berlekamp's table keeps one
+// polynomial coefficient per lane (degree <= 2t-1 < 32) so the discrepancy is a warp XOR
+// reduction and the polynomial update a shuffle.  The Chien search strides the n exponents
+// over the lanes in the log domain.  log/antilog tables (2 x 2^m uint16) are read through
+// the read-only path and stay L1/L2 resident.
+//
+// Where the reference would throw out of general_work (closed-form degree-1/2 roots landing
+// outside the shortened code, lib/bch.cc:441 / lib/gf.h:110 -- needs > t errors imitating a
+// 1- or 2-error syndrome), this kernel reports -1 and flips nothing.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace dvbs2b200 {
+
+namespace {
+
+constexpr int kMaxT = 12;
+constexpr unsigned kFull = 0xffffffffu;
+
+struct Gf {
+    const uint16_t* __restrict__ antilog;
+    const uint16_t* __restrict__ log;
+    uint32_t nz; // 2^m - 1
+    int m;
+    __device__ __forceinline__ uint32_t fold(uint32_t x) const
+    { // x mod (2^m - 1) for x < 2^(2m)
+        x = (x & nz) + (x >> m);
+        x = (x & nz) + (x >> m);
+        return x >= nz ? x - nz : x;
+    }
+    __device__ __forceinline__ uint32_t alpha(uint32_t e) const { return __ldg(antilog + e); } // e <= nz
+    __device__ __forceinline__ uint32_t mul(uint32_t a, uint32_t b) const
+    {
+        if (!a || !b)
+            return 0;
+        uint32_t e = (uint32_t)__ldg(log + a) + (uint32_t)__ldg(log + b);
+        return alpha(e >= nz ? e - nz : e);
+    }
+    __device__ __forceinline__ uint32_t div(uint32_t a, uint32_t b) const
+    { // b != 0
+        if (!a)
+            return 0;
+        uint32_t e = (uint32_t)__ldg(log + a) + nz - (uint32_t)__ldg(log + b);
+        return alpha(e >= nz ? e - nz : e);
+    }
+};
+
+__device__ __forceinline__ uint32_t warp_xor(uint32_t v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v ^= __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(kBchWarpsPerBlock * 32) bch_decode_kernel(const BchLaunch p)
+{
+    // per-warp scratch: Berlekamp rows [t+2][32 coefficients], syndromes, root list
+    __shared__ uint16_t s_sig[kBchWarpsPerBlock][kMaxT + 2][32];
+    __shared__ uint16_t s_S[kBchWarpsPerBlock][2 * kMaxT];
+    __shared__ uint32_t s_roots[kBchWarpsPerBlock][kMaxT + 1];
+    __shared__ int s_nroots[kBchWarpsPerBlock];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int frame = blockIdx.x * kBchWarpsPerBlock + warp;
+    if (frame >= p.frames)
+        return;
+    Gf gf;
+    gf.antilog = p.antilog;
+    gf.log = p.log;
+    gf.m = p.m;
+    gf.nz = (1u << p.m) - 1u;
+    const int n = p.n, k = p.k, t = p.t;
+    const int n_bytes = n >> 3, k_bytes = k >> 3;
+    const uint8_t* __restrict__ cw = p.cw + (size_t)frame * p.cw_stride;
+    uint8_t* __restrict__ msg = p.msg + (size_t)frame * p.msg_stride;
+
+    // ---- systematic copy (lib/bch.cc:471) + odd syndromes -----------------------------------
+    uint32_t S_odd[kMaxT];
+#pragma unroll
+    for (int i = 0; i < kMaxT; ++i)
+        S_odd[i] = 0;
+    for (int y = lane; y < n_bytes; y += 32) {
+        const uint32_t byte = __ldg(cw + y);
+        if (y < k_bytes)
+            msg[y] = (uint8_t)byte;
+        if (!byte)
+            continue;
+        // bit kbit (0 = MSB) of byte y is the coefficient of x^(n - 1 - 8y - kbit)
+        const uint32_t p0 = (uint32_t)(n - 1 - 8 * y);
+#pragma unroll
+        for (int i = 0; i < kMaxT; ++i) {
+            if (i < t) {
+                const uint32_t a = (uint32_t)(2 * i + 1);
+                uint32_t e = gf.fold(a * p0); // exponent of alpha^(a * p0)
+                uint32_t acc = 0;
+#pragma unroll
+                for (int kb = 0; kb < 8; ++kb) {
+                    if (byte & (0x80u >> kb))
+                        acc ^= gf.alpha(e);
+                    e = (e >= a) ? e - a : e + gf.nz - a; // next lower power
+                }
+                S_odd[i] ^= acc;
+            }
+        }
+    }
+    uint32_t any = 0;
+#pragma unroll
+    for (int i = 0; i < kMaxT; ++i) {
+        S_odd[i] = warp_xor(S_odd[i]);
+        any |= S_odd[i];
+    }
+    __syncwarp();
+    if (!any) { // lib/bch.cc:179-180: zero remainder <=> all syndromes zero -> no errors
+        if (lane == 0 && p.corrections)
+            p.corrections[frame] = 0;
+        return;
+    }
+    // S[0..2t) = S_1..S_2t; S_2j = S_j^2
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kMaxT; ++i)
+            if (i < t)
+                s_S[warp][2 * i] = (uint16_t)S_odd[i];
+        for (int j = 1; j <= t; ++j) { // S_{2j} from S_j (ascending j: S_j already known)
+            const uint32_t sj = s_S[warp][j - 1];
+            s_S[warp][2 * j - 1] = (uint16_t)gf.mul(sj, sj);
+        }
+    }
+    __syncwarp();
+    const uint16_t* S = s_S[warp];
+
+    // ---- Berlekamp, table form (lib/bch.cc:224-304); lane = coefficient index -----------------
+    int deg[kMaxT + 3];
+    int two_mu[kMaxT + 3];
+    uint32_t dis[kMaxT + 3];
+    two_mu[0] = -1;
+#pragma unroll
+    for (int i = 0; i < kMaxT + 2; ++i)
+        two_mu[i + 1] = 2 * i;
+    s_sig[warp][0][lane] = (lane == 0);
+    s_sig[warp][1][lane] = (lane == 0);
+    s_sig[warp][2][lane] = (lane == 0) ? 1 : (lane == 1 ? S[0] : 0);
+    deg[0] = 0;
+    deg[1] = 0;
+    deg[2] = S[0] ? 1 : 0;
+    dis[0] = 1;
+    dis[1] = S[0];
+    __syncwarp();
+    int row = 2;
+    for (; row <= t; ++row) {
+        const int tm = two_mu[row];
+        const uint32_t cur = s_sig[warp][row][lane];
+        uint32_t term = 0;
+        if (lane >= 1 && lane <= deg[row] && lane <= tm && cur)
+            term = gf.mul(cur, S[tm - lane]);
+        const uint32_t d = (uint32_t)S[tm] ^ warp_xor(term);
+        dis[row] = d;
+        uint32_t nxt = cur;
+        if (d != 0) {
+            int row_rho = 0, max_diff = -2;
+            for (int j = row - 1; j >= 0; --j) // latest row wins ties (strict >)
+                if (dis[j] != 0) {
+                    const int diff = two_mu[j] - deg[j];
+                    if (diff > max_diff) {
+                        max_diff = diff;
+                        row_rho = j;
+                    }
+                }
+            const uint32_t coef = gf.div(d, dis[row_rho]);
+            const int shift = tm - two_mu[row_rho];
+            if (lane >= shift)
+                nxt ^= gf.mul(coef, s_sig[warp][row_rho][lane - shift]);
+        }
+        s_sig[warp][row + 1][lane] = (uint16_t)nxt;
+        const unsigned nzmask = __ballot_sync(kFull, nxt != 0);
+        deg[row + 1] = nzmask ? 31 - __clz((int)nzmask) : -1;
+        __syncwarp();
+    }
+    const int L = deg[row];
+    const uint32_t my_sigma = s_sig[warp][row][lane];
+
+    // ---- roots (lib/bch.cc:306-385) --------------------------------------------------------------
+    if (lane == 0)
+        s_nroots[warp] = 0;
+    __syncwarp();
+    int found = 0;
+    if (L >= 1 && L <= t) {
+        // sigma(alpha^e) = XOR_j alpha^(log sigma_j + e*j); lanes take e = s+1+lane, +32, ...
+        uint32_t lg[kMaxT + 1], acc[kMaxT + 1], step[kMaxT + 1];
+        bool on[kMaxT + 1];
+        const uint32_t e0 = p.shorten + 1u + (uint32_t)lane;
+#pragma unroll
+        for (int j = 0; j <= kMaxT; ++j) {
+            const uint32_t sj = __shfl_sync(kFull, my_sigma, j);
+            on[j] = (j <= L) && (sj != 0);
+            lg[j] = on[j] ? (uint32_t)__ldg(gf.log + sj) : 0u;
+            acc[j] = gf.fold(lg[j] + gf.fold(e0 * (uint32_t)j));
+            step[j] = gf.fold(32u * (uint32_t)j);
+        }
+        const uint32_t e_end = (uint32_t)n + p.shorten; // inclusive
+        for (uint32_t e = e0; e <= e_end; e += 32) {
+            uint32_t res = 0;
+#pragma unroll
+            for (int j = 0; j <= kMaxT; ++j) {
+                if (on[j]) {
+                    res ^= gf.alpha(acc[j]);
+                    uint32_t a = acc[j] + step[j];
+                    acc[j] = a >= gf.nz ? a - gf.nz : a;
+                }
+            }
+            if (res == 0) {
+                const int slot = atomicAdd(&s_nroots[warp], 1);
+                if (slot <= kMaxT)
+                    s_roots[warp][slot] = e;
+            }
+        }
+        __syncwarp();
+        found = s_nroots[warp];
+    }
+
+    // ---- flips (lib/bch.cc:428-452) and return code (:476-483) -----------------------------------
+    const bool closed_form_failure = (L <= 2) && (found != L); // reference throws / returns {} here
+    if (lane == 0) {
+        if (!closed_form_failure) {
+            for (int r = 0; r < found && r <= kMaxT; ++r) {
+                const uint32_t bit_idx = gf.nz - s_roots[warp][r]; // locator exponent, in [0, n)
+                if (bit_idx < (uint32_t)(n - k))
+                    continue; // parity bit: the message is all that is emitted
+                const uint32_t net = (uint32_t)n - 1u - bit_idx;
+                msg[net >> 3] ^= (uint8_t)(1u << (7u - (net & 7u)));
+            }
+        }
+        if (p.corrections)
+            p.corrections[frame] = (found == L && L >= 1) ? found : -1;
+    }
+}
+
+} // namespace
+
+cudaError_t bch_launch(const BchLaunch& p, cudaStream_t stream)
+{
+    if (p.frames <= 0)
+        return cudaSuccess;
+    if (p.t > kMaxT)
+        return cudaErrorInvalidValue;
+    const int blocks = (p.frames + kBchWarpsPerBlock - 1) / kBchWarpsPerBlock;
+    bch_decode_kernel<<<blocks, kBchWarpsPerBlock * 32, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+} // namespace dvbs2b200

@@ -1,0 +1,673 @@
+// capi.cu -- the C ABI of libdvbs2_b200.so (include/dvbs2_b200.h): handles, staging, launches.
+// No CPU fallback: without a CUDA device every compute entry point fails with DVBS2B200_ECUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/dvbs2_b200.h"
+#include "code_tables.h"
+#include "kernels.h"
+
+using namespace dvbs2b200;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what)
+{
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return DVBS2B200_ECUDA;
+}
+#define CU(call)                             \
+    do {                                     \
+        cudaError_t e__ = (call);            \
+        if (e__ != cudaSuccess)              \
+            return cuda_fail(e__, #call);    \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap)
+            return DVBS2B200_OK;
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            g_err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+            return DVBS2B200_ENOMEM;
+        }
+        cap = want;
+        return DVBS2B200_OK;
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+} // namespace
+
+struct dvbs2b200_code {
+    int device = 0;
+    int sm_count = 0;
+    int smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<uint8_t> blob;
+    BlobHeader hdr;
+    uint8_t* d_blob = nullptr;
+    size_t ldpc_smem = 0;
+    uint64_t launches = 0;
+    // staging for the host-pointer entry points
+    DevBuf d_in, d_mid, d_out, d_post, d_i32a, d_i32b, d_n0, d_llr, d_sync;
+};
+
+namespace {
+
+void info_from_header(const BlobHeader& h, dvbs2b200_code_info* info)
+{
+    info->table = h.table;
+    info->n_ldpc = h.N;
+    info->k_ldpc = h.K;
+    info->q = h.q;
+    info->n_circ = h.n_circ;
+    info->links_total = h.links_total;
+    info->max_cn_deg = h.max_cn_deg;
+    info->kbch = h.kbch;
+    info->nbch = h.nbch;
+    info->t = h.t;
+    info->gf_m = h.gf_m;
+}
+
+int create_from_blob(dvbs2b200_code** out, int device, std::vector<uint8_t>&& blob)
+{
+    std::string err;
+    if (!validate_blob(blob.data(), blob.size(), err))
+        return fail(DVBS2B200_EINVAL, err);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(DVBS2B200_ECUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                                         "); libdvbs2_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev)
+        return fail(DVBS2B200_EINVAL, "device index out of range");
+    dvbs2b200_code* h = new (std::nothrow) dvbs2b200_code();
+    if (!h)
+        return fail(DVBS2B200_ENOMEM, "out of host memory");
+    h->device = device;
+    h->blob = std::move(blob);
+    memcpy(&h->hdr, h->blob.data(), sizeof(BlobHeader));
+    auto bail = [&](int code) {
+        dvbs2b200_code_destroy(h);
+        return code;
+    };
+    if (cudaSetDevice(device) != cudaSuccess)
+        return bail(fail(DVBS2B200_ECUDA, "cudaSetDevice failed"));
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail(cuda_fail(e, "cudaStreamCreate"));
+    if ((e = cudaMalloc((void**)&h->d_blob, h->blob.size())) != cudaSuccess)
+        return bail(cuda_fail(e, "cudaMalloc(tables)"));
+    if ((e = cudaMemcpy(h->d_blob, h->blob.data(), h->blob.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return bail(cuda_fail(e, "cudaMemcpy(tables)"));
+    h->ldpc_smem = ldpc_smem_bytes(h->hdr.N, h->hdr.R, h->hdr.msg_words, h->hdr.smem_bytes, nullptr);
+    *out = h;
+    return DVBS2B200_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev)
+            cudaSetDevice(dev);
+        else
+            prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0)
+            cudaSetDevice(prev);
+    }
+};
+
+int ldpc_out_bytes(const BlobHeader& h, int output_mode) { return (output_mode ? h.kldpc_out : h.N) / 8; }
+
+// grid size: one persistent CTA per SM; in group mode a multiple of the group that fits the SMs
+int ldpc_grid(const dvbs2b200_code* h, int frames, int group)
+{
+    int grid = std::min(frames, h->sm_count);
+    if (group > 1)
+        grid = std::min(frames, (h->sm_count / group) * group);
+    return grid;
+}
+
+int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials, int term_group, int output_mode,
+             uint8_t* d_hard, int8_t* d_llr_post, int32_t* d_trials_left, cudaStream_t stream)
+{
+    const BlobHeader& hd = h->hdr;
+    if (frames < 0 || max_trials < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames/max_trials");
+    if (frames == 0)
+        return DVBS2B200_OK;
+    if (!d_llr)
+        return fail(DVBS2B200_EINVAL, "llr is null");
+    if (term_group != 0 && term_group != 1 && term_group != 16 && term_group != 32)
+        return fail(DVBS2B200_EINVAL, "term_group must be 0, 16 or 32");
+    if (term_group > 1 && frames % term_group)
+        return fail(DVBS2B200_EINVAL, "frames must be a multiple of term_group");
+    if (term_group > 1 && h->sm_count < term_group)
+        return fail(DVBS2B200_EUNSUPPORTED, "device has fewer SMs than term_group");
+    if (h->ldpc_smem > (size_t)h->smem_optin)
+        return fail(DVBS2B200_EUNSUPPORTED,
+                    "this code needs more shared memory per CTA than the device offers (low-rate normal frames: "
+                    "packed 24-bit check-node state not built yet)");
+    if (hd.max_cnt > 28)
+        return fail(DVBS2B200_EUNSUPPORTED, "check-node degree above 30");
+    if (max_trials == 0)
+        max_trials = 25; // lib/ldpc_decoder_bb_impl.cc:391,402
+    LdpcLaunch p;
+    memset(&p, 0, sizeof(p));
+    p.N = hd.N;
+    p.K = hd.K;
+    p.R = hd.R;
+    p.q = hd.q;
+    p.tab = h->d_blob + hd.smem_off;
+    p.tab_bytes = hd.smem_bytes;
+    p.steps = reinterpret_cast<const StepRecDev*>(h->d_blob + hd.step_off);
+    p.order = reinterpret_cast<const uint16_t*>(h->d_blob + hd.order_off);
+    size_t smem = ldpc_smem_bytes(hd.N, hd.R, hd.msg_words, hd.smem_bytes, &p);
+    p.llr = d_llr;
+    p.frames = frames;
+    p.max_trials = max_trials;
+    p.group = term_group > 1 ? term_group : 0;
+    p.hard = d_hard;
+    p.out_bytes = ldpc_out_bytes(hd, output_mode);
+    p.llr_post = d_llr_post;
+    p.trials_left = d_trials_left;
+    if (p.group) {
+        size_t words = (size_t)(frames / p.group) * (max_trials + 2);
+        int rc = h->d_sync.ensure(words * sizeof(unsigned));
+        if (rc)
+            return rc;
+        CU(cudaMemsetAsync(h->d_sync.p, 0, words * sizeof(unsigned), stream));
+        p.gsync = (unsigned*)h->d_sync.p;
+    }
+    cudaError_t e = ldpc_launch(p, hd.max_cnt, hd.msg_words, ldpc_grid(h, frames, p.group), smem, stream);
+    if (e != cudaSuccess)
+        return cuda_fail(e, "ldpc_launch");
+    h->launches += 1;
+    return DVBS2B200_OK;
+}
+
+int bch_dev(dvbs2b200_code* h, const uint8_t* d_cw, int cw_stride, int frames, uint8_t* d_msg, int32_t* d_corr,
+            cudaStream_t stream)
+{
+    const BlobHeader& hd = h->hdr;
+    if (frames < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames");
+    if (frames == 0)
+        return DVBS2B200_OK;
+    if (!d_cw || !d_msg)
+        return fail(DVBS2B200_EINVAL, "null buffer");
+    if (hd.kbch <= 0 || hd.kbch % 8 || hd.nbch % 8)
+        return fail(DVBS2B200_EUNSUPPORTED, "BCH k and n must be multiples of 8 (lib/bch.cc:19-24)");
+    BchLaunch p;
+    memset(&p, 0, sizeof(p));
+    p.cw = d_cw;
+    p.msg = d_msg;
+    p.corrections = d_corr;
+    p.frames = frames;
+    p.n = hd.nbch;
+    p.k = hd.kbch;
+    p.t = hd.t;
+    p.m = hd.gf_m;
+    p.shorten = hd.bch_shorten;
+    p.antilog = reinterpret_cast<const uint16_t*>(h->d_blob + hd.antilog_off);
+    p.log = reinterpret_cast<const uint16_t*>(h->d_blob + hd.log_off);
+    p.cw_stride = cw_stride;
+    p.msg_stride = hd.kbch / 8;
+    cudaError_t e = bch_launch(p, stream);
+    if (e != cudaSuccess)
+        return cuda_fail(e, "bch_launch");
+    h->launches += 1;
+    return DVBS2B200_OK;
+}
+
+int bits_per_symbol(int constellation)
+{
+    if (constellation == 0)
+        return 2; // MOD_QPSK
+    if (constellation == 4)
+        return 3; // MOD_8PSK
+    return 0;
+}
+
+int demap_dev(dvbs2b200_code* h, int constellation, const float* d_iq, int frames, const float* d_n0, int8_t* d_llr,
+              cudaStream_t stream)
+{
+    const BlobHeader& hd = h->hdr;
+    const int bits = bits_per_symbol(constellation);
+    if (!bits) // lib/xfecframe_demapper_cb_impl.cc:70-72
+        return fail(DVBS2B200_EUNSUPPORTED, "Unsupported constellation");
+    if (frames < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames");
+    if (frames == 0)
+        return DVBS2B200_OK;
+    if (!d_iq || !d_n0 || !d_llr)
+        return fail(DVBS2B200_EINVAL, "null buffer");
+    DemapLaunch p;
+    memset(&p, 0, sizeof(p));
+    p.n_syms = hd.N / bits;
+    p.constellation = constellation;
+    if (constellation == 4) {
+        const int rows = p.n_syms, rate = hd.rate; // lib/xfecframe_demapper_cb_impl.cc:48-69
+        if (rate == 4) { // C3_5
+            p.row0 = rows * 2, p.row1 = rows, p.row2 = 0;
+        } else if (rate == 26 || rate == 28 || rate == 38 || rate == 39 || rate == 19) {
+            p.row0 = rows, p.row1 = 0, p.row2 = rows * 2; // C25_36 C13_18 C7_15 C8_15 C26_45
+        } else {
+            p.row0 = 0, p.row1 = rows, p.row2 = rows * 2;
+        }
+    }
+    for (int f0 = 0; f0 < frames; f0 += 32768) { // gridDim.y limit
+        p.frames = std::min(32768, frames - f0);
+        p.iq = d_iq + (size_t)f0 * p.n_syms * 2;
+        p.n0 = d_n0 + f0;
+        p.llr = d_llr + (size_t)f0 * hd.N;
+        cudaError_t e = demap_launch(p, stream);
+        if (e != cudaSuccess)
+            return cuda_fail(e, "demap_launch");
+        h->launches += 1;
+    }
+    return DVBS2B200_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int dvbs2b200_version(void) { return DVBS2B200_VERSION; }
+const char* dvbs2b200_last_error(void) { return g_err.c_str(); }
+
+int dvbs2b200_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver)
+        return 0;
+    if (e != cudaSuccess)
+        return cuda_fail(e, "cudaGetDeviceCount");
+    return n;
+}
+
+int dvbs2b200_num_tables(void) { return num_tables(); }
+const char* dvbs2b200_table_name(int table)
+{
+    const LdpcTableDef* d = table_def(table);
+    return d ? d->name : nullptr;
+}
+
+int dvbs2b200_lookup(int standard, int framesize, int rate, dvbs2b200_code_info* info)
+{
+    const ModcodDef* mc = find_modcod(standard, framesize, rate);
+    if (!mc)
+        return fail(DVBS2B200_EUNSUPPORTED, "no LDPC table for this (standard, framesize, rate)");
+    if (info) {
+        const LdpcTableDef* d = table_def(mc->table);
+        Schedule s;
+        build_schedule(*d, s);
+        info->table = mc->table;
+        info->n_ldpc = d->N;
+        info->k_ldpc = d->K;
+        info->q = d->q;
+        info->n_circ = d->n_circ;
+        info->links_total = d->links_total;
+        info->max_cn_deg = s.max_cnt + 2;
+        info->kbch = mc->kbch;
+        info->nbch = mc->nbch;
+        info->t = mc->t;
+        info->gf_m = framesize == 1 ? 16 : framesize == 0 ? 14 : 15;
+    }
+    return DVBS2B200_OK;
+}
+
+int dvbs2b200_table_circulants(int table, uint32_t* out, int cap)
+{
+    const LdpcTableDef* d = table_def(table);
+    if (!d)
+        return fail(DVBS2B200_EINVAL, "bad table index");
+    for (int i = 0; i < d->n_circ && i < cap; ++i)
+        out[i] = d->circ[i];
+    return d->n_circ;
+}
+
+int dvbs2b200_bch_genpoly(int framesize, int t, uint8_t* g, int cap)
+{
+    if (t < 1 || t > 12)
+        return fail(DVBS2B200_EINVAL, "t out of range");
+    std::vector<uint8_t> gp = bch_genpoly(bch_prim_poly(framesize), t);
+    for (size_t i = 0; i < gp.size() && (int)i < cap; ++i)
+        g[i] = gp[i];
+    return (int)gp.size() - 1;
+}
+
+int dvbs2b200_schedule_stats(int table, int* steps_per_iter, int* max_depth, int* conflict_layers)
+{
+    const LdpcTableDef* d = table_def(table);
+    if (!d)
+        return fail(DVBS2B200_EINVAL, "bad table index");
+    Schedule s;
+    build_schedule(*d, s);
+    if (steps_per_iter)
+        *steps_per_iter = s.steps_per_iter;
+    if (max_depth)
+        *max_depth = s.max_depth;
+    if (conflict_layers)
+        *conflict_layers = s.conflict_layers;
+    return DVBS2B200_OK;
+}
+
+int dvbs2b200_code_create(dvbs2b200_code** h, int device, int standard, int framesize, int rate)
+{
+    if (!h)
+        return fail(DVBS2B200_EINVAL, "null handle pointer");
+    *h = nullptr;
+    std::vector<uint8_t> blob;
+    std::string err;
+    if (!build_blob(standard, framesize, rate, blob, err))
+        return fail(DVBS2B200_EUNSUPPORTED, err);
+    return create_from_blob(h, device, std::move(blob));
+}
+
+int dvbs2b200_code_create_from_tables(dvbs2b200_code** h, int device, const void* blob, size_t size)
+{
+    if (!h || !blob)
+        return fail(DVBS2B200_EINVAL, "null argument");
+    *h = nullptr;
+    std::vector<uint8_t> copy((const uint8_t*)blob, (const uint8_t*)blob + size);
+    return create_from_blob(h, device, std::move(copy));
+}
+
+int dvbs2b200_code_export_tables(const dvbs2b200_code* h, void* buf, size_t cap, size_t* size)
+{
+    if (!h)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    if (size)
+        *size = h->blob.size();
+    if (buf) {
+        if (cap < h->blob.size())
+            return fail(DVBS2B200_EINVAL, "buffer too small");
+        memcpy(buf, h->blob.data(), h->blob.size());
+    }
+    return DVBS2B200_OK;
+}
+
+void dvbs2b200_code_destroy(dvbs2b200_code* h)
+{
+    if (!h)
+        return;
+    DeviceGuard g(h->device);
+    if (h->stream)
+        cudaStreamSynchronize(h->stream);
+    for (DevBuf* b : { &h->d_in, &h->d_mid, &h->d_out, &h->d_post, &h->d_i32a, &h->d_i32b, &h->d_n0, &h->d_llr, &h->d_sync })
+        b->release();
+    if (h->d_blob)
+        cudaFree(h->d_blob);
+    if (h->stream)
+        cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int dvbs2b200_code_info_get(const dvbs2b200_code* h, dvbs2b200_code_info* info)
+{
+    if (!h || !info)
+        return fail(DVBS2B200_EINVAL, "null argument");
+    info_from_header(h->hdr, info);
+    return DVBS2B200_OK;
+}
+
+uint64_t dvbs2b200_launch_count(const dvbs2b200_code* h) { return h ? h->launches : 0; }
+
+// ---- LDPC -------------------------------------------------------------------------------------
+int dvbs2b200_ldpc_decode_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials, int term_group,
+                              int output_mode, uint8_t* d_hard, int8_t* d_llr_post, int32_t* d_trials_left,
+                              void* stream)
+{
+    if (!h)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    DeviceGuard g(h->device);
+    return ldpc_dev(h, d_llr, frames, max_trials, term_group, output_mode, d_hard, d_llr_post, d_trials_left,
+                    (cudaStream_t)stream);
+}
+
+int dvbs2b200_ldpc_decode(dvbs2b200_code* h, const int8_t* llr, int frames, int max_trials, int term_group,
+                          int output_mode, uint8_t* hard, int8_t* llr_post, int32_t* trials_left)
+{
+    if (!h)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    if (frames < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames");
+    if (frames == 0)
+        return DVBS2B200_OK;
+    if (!llr)
+        return fail(DVBS2B200_EINVAL, "llr is null");
+    DeviceGuard g(h->device);
+    const BlobHeader& hd = h->hdr;
+    const size_t in_bytes = (size_t)frames * hd.N;
+    const size_t out_bytes = (size_t)frames * ldpc_out_bytes(hd, output_mode);
+    int rc;
+    if ((rc = h->d_in.ensure(in_bytes)))
+        return rc;
+    if (hard && (rc = h->d_out.ensure(out_bytes)))
+        return rc;
+    if (llr_post && (rc = h->d_post.ensure(in_bytes)))
+        return rc;
+    if (trials_left && (rc = h->d_i32a.ensure((size_t)frames * 4)))
+        return rc;
+    cudaStream_t s = h->stream;
+    CU(cudaMemcpyAsync(h->d_in.p, llr, in_bytes, cudaMemcpyHostToDevice, s));
+    rc = ldpc_dev(h, (const int8_t*)h->d_in.p, frames, max_trials, term_group, output_mode,
+                  hard ? (uint8_t*)h->d_out.p : nullptr, llr_post ? (int8_t*)h->d_post.p : nullptr,
+                  trials_left ? (int32_t*)h->d_i32a.p : nullptr, s);
+    if (rc)
+        return rc;
+    if (hard)
+        CU(cudaMemcpyAsync(hard, h->d_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+    if (llr_post)
+        CU(cudaMemcpyAsync(llr_post, h->d_post.p, in_bytes, cudaMemcpyDeviceToHost, s));
+    if (trials_left)
+        CU(cudaMemcpyAsync(trials_left, h->d_i32a.p, (size_t)frames * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return DVBS2B200_OK;
+}
+
+// ---- BCH --------------------------------------------------------------------------------------
+int dvbs2b200_bch_decode_dev(dvbs2b200_code* h, const uint8_t* d_cw, int frames, uint8_t* d_msg,
+                             int32_t* d_corrections, void* stream)
+{
+    if (!h)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    DeviceGuard g(h->device);
+    return bch_dev(h, d_cw, h->hdr.nbch / 8, frames, d_msg, d_corrections, (cudaStream_t)stream);
+}
+
+int dvbs2b200_bch_decode(dvbs2b200_code* h, const uint8_t* cw, int frames, uint8_t* msg, int32_t* corrections)
+{
+    if (!h)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    if (frames < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames");
+    if (frames == 0)
+        return DVBS2B200_OK;
+    if (!cw || !msg)
+        return fail(DVBS2B200_EINVAL, "null buffer");
+    DeviceGuard g(h->device);
+    const BlobHeader& hd = h->hdr;
+    const size_t in_bytes = (size_t)frames * (hd.nbch / 8), out_bytes = (size_t)frames * (hd.kbch / 8);
+    int rc;
+    if ((rc = h->d_mid.ensure(in_bytes)) || (rc = h->d_out.ensure(out_bytes)) ||
+        (rc = h->d_i32b.ensure((size_t)frames * 4)))
+        return rc;
+    cudaStream_t s = h->stream;
+    CU(cudaMemcpyAsync(h->d_mid.p, cw, in_bytes, cudaMemcpyHostToDevice, s));
+    rc = bch_dev(h, (const uint8_t*)h->d_mid.p, hd.nbch / 8, frames, (uint8_t*)h->d_out.p, (int32_t*)h->d_i32b.p, s);
+    if (rc)
+        return rc;
+    CU(cudaMemcpyAsync(msg, h->d_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+    if (corrections)
+        CU(cudaMemcpyAsync(corrections, h->d_i32b.p, (size_t)frames * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return DVBS2B200_OK;
+}
+
+// ---- demapper ---------------------------------------------------------------------------------
+int dvbs2b200_demap_dev(dvbs2b200_code* h, int constellation, const float* d_iq, int frames, const float* d_n0,
+                        int8_t* d_llr, void* stream)
+{
+    if (!h)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    DeviceGuard g(h->device);
+    return demap_dev(h, constellation, d_iq, frames, d_n0, d_llr, (cudaStream_t)stream);
+}
+
+int dvbs2b200_demap(dvbs2b200_code* h, int constellation, const float* iq, int frames, const float* n0, int8_t* llr)
+{
+    if (!h)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    const int bits = bits_per_symbol(constellation);
+    if (!bits)
+        return fail(DVBS2B200_EUNSUPPORTED, "Unsupported constellation");
+    if (frames < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames");
+    if (frames == 0)
+        return DVBS2B200_OK;
+    if (!iq || !n0 || !llr)
+        return fail(DVBS2B200_EINVAL, "null buffer");
+    DeviceGuard g(h->device);
+    const BlobHeader& hd = h->hdr;
+    const size_t iq_bytes = (size_t)frames * (hd.N / bits) * 8, llr_bytes = (size_t)frames * hd.N;
+    int rc;
+    if ((rc = h->d_in.ensure(iq_bytes)) || (rc = h->d_llr.ensure(llr_bytes)) || (rc = h->d_n0.ensure((size_t)frames * 4)))
+        return rc;
+    cudaStream_t s = h->stream;
+    CU(cudaMemcpyAsync(h->d_in.p, iq, iq_bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->d_n0.p, n0, (size_t)frames * 4, cudaMemcpyHostToDevice, s));
+    rc = demap_dev(h, constellation, (const float*)h->d_in.p, frames, (const float*)h->d_n0.p, (int8_t*)h->d_llr.p, s);
+    if (rc)
+        return rc;
+    CU(cudaMemcpyAsync(llr, h->d_llr.p, llr_bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return DVBS2B200_OK;
+}
+
+// ---- fused chain ------------------------------------------------------------------------------
+int dvbs2b200_fec_decode_dev(dvbs2b200_code* h, int constellation, const float* d_iq, const float* d_n0,
+                             const int8_t* d_llr, int frames, int max_trials, int term_group, uint8_t* d_msg,
+                             int32_t* d_trials_left, int32_t* d_corrections, void* stream)
+{
+    if (!h)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    if (frames < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames");
+    if (frames == 0)
+        return DVBS2B200_OK;
+    if (!d_msg || (!d_iq && !d_llr))
+        return fail(DVBS2B200_EINVAL, "null buffer");
+    DeviceGuard g(h->device);
+    const BlobHeader& hd = h->hdr;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if (d_iq) {
+        if ((rc = h->d_llr.ensure((size_t)frames * hd.N)))
+            return rc;
+        if ((rc = demap_dev(h, constellation, d_iq, frames, d_n0, (int8_t*)h->d_llr.p, s)))
+            return rc;
+        d_llr = (const int8_t*)h->d_llr.p;
+    }
+    const int mid_stride = hd.kldpc_out / 8; // OM_MESSAGE: BCH codeword bytes
+    if ((rc = h->d_mid.ensure((size_t)frames * mid_stride)))
+        return rc;
+    if ((rc = ldpc_dev(h, d_llr, frames, max_trials, term_group, /*OM_MESSAGE*/ 1, (uint8_t*)h->d_mid.p, nullptr,
+                       d_trials_left, s)))
+        return rc;
+    return bch_dev(h, (const uint8_t*)h->d_mid.p, mid_stride, frames, d_msg, d_corrections, s);
+}
+
+int dvbs2b200_fec_decode(dvbs2b200_code* h, int constellation, const float* iq, const float* n0, const int8_t* llr,
+                         int frames, int max_trials, int term_group, uint8_t* msg, int32_t* trials_left,
+                         int32_t* corrections)
+{
+    if (!h)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    if (frames < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames");
+    if (frames == 0)
+        return DVBS2B200_OK;
+    if (!msg || (!iq && !llr))
+        return fail(DVBS2B200_EINVAL, "null buffer");
+    if (iq && !n0)
+        return fail(DVBS2B200_EINVAL, "n0 is null");
+    DeviceGuard g(h->device);
+    const BlobHeader& hd = h->hdr;
+    cudaStream_t s = h->stream;
+    int rc;
+    const float* d_iq = nullptr;
+    const float* d_n0 = nullptr;
+    const int8_t* d_llr = nullptr;
+    if (iq) {
+        const int bits = bits_per_symbol(constellation);
+        if (!bits)
+            return fail(DVBS2B200_EUNSUPPORTED, "Unsupported constellation");
+        const size_t iq_bytes = (size_t)frames * (hd.N / bits) * 8;
+        if ((rc = h->d_in.ensure(iq_bytes)) || (rc = h->d_n0.ensure((size_t)frames * 4)))
+            return rc;
+        CU(cudaMemcpyAsync(h->d_in.p, iq, iq_bytes, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(h->d_n0.p, n0, (size_t)frames * 4, cudaMemcpyHostToDevice, s));
+        d_iq = (const float*)h->d_in.p;
+        d_n0 = (const float*)h->d_n0.p;
+    } else {
+        if ((rc = h->d_in.ensure((size_t)frames * hd.N)))
+            return rc;
+        CU(cudaMemcpyAsync(h->d_in.p, llr, (size_t)frames * hd.N, cudaMemcpyHostToDevice, s));
+        d_llr = (const int8_t*)h->d_in.p;
+    }
+    const size_t out_bytes = (size_t)frames * (hd.kbch / 8);
+    if ((rc = h->d_out.ensure(out_bytes)) || (rc = h->d_i32a.ensure((size_t)frames * 4)) ||
+        (rc = h->d_i32b.ensure((size_t)frames * 4)))
+        return rc;
+    rc = dvbs2b200_fec_decode_dev(h, constellation, d_iq, d_n0, d_llr, frames, max_trials, term_group,
+                                  (uint8_t*)h->d_out.p, (int32_t*)h->d_i32a.p, (int32_t*)h->d_i32b.p, s);
+    if (rc)
+        return rc;
+    CU(cudaMemcpyAsync(msg, h->d_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+    if (trials_left)
+        CU(cudaMemcpyAsync(trials_left, h->d_i32a.p, (size_t)frames * 4, cudaMemcpyDeviceToHost, s));
+    if (corrections)
+        CU(cudaMemcpyAsync(corrections, h->d_i32b.p, (size_t)frames * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return DVBS2B200_OK;
+}
+
+} // extern "C"

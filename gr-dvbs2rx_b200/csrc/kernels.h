@@ -1,0 +1,63 @@
+// kernels.h -- launch descriptors shared by the sm_100a kernels and the C ABI (capi.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dvbs2b200 {
+
+constexpr int kLdpcThreads = 384; // 360 check nodes of a layer + 24 spare lanes = 12 warps
+
+struct StepRecDev {
+    uint16_t begin, count;
+};
+
+struct LdpcLaunch {
+    // code
+    int N, K, R, q;
+    const uint8_t* tab;  // device: [LayerRec q][edge words], 16-byte aligned
+    uint32_t tab_bytes;  // multiple of 16
+    const StepRecDev* steps;
+    const uint16_t* order;
+    // shared-memory carve-up (bytes from the start of dynamic shared memory)
+    uint32_t smem_msg_off, smem_tab_off, smem_bar_off;
+    // batch
+    const int8_t* llr; // [frames][N]
+    int frames;
+    int max_trials;
+    int group;           // 0/1 per-frame termination, else frames per coupled group
+    unsigned int* gsync; // [frames/group][max_trials + 2], zeroed (group mode only)
+    uint8_t* hard;       // [frames][out_bytes] or null
+    int out_bytes;
+    int8_t* llr_post;     // [frames][N] or null
+    int32_t* trials_left; // [frames] or null
+};
+
+// fills the smem_* offsets of p (if non-null) and returns the dynamic shared memory size
+size_t ldpc_smem_bytes(int N, int R, int msg_words, uint32_t tab_bytes, LdpcLaunch* p);
+cudaError_t ldpc_launch(const LdpcLaunch& p, int max_cnt, int msg_words, int grid, size_t smem, cudaStream_t stream);
+
+struct BchLaunch {
+    const uint8_t* cw; // [frames][n_bytes]
+    uint8_t* msg;      // [frames][k_bytes]
+    int32_t* corrections; // [frames] or null
+    int frames;
+    int n, k, t, m;    // bits, bits, capability, GF(2^m)
+    uint32_t shorten;  // s = 2^m - 1 - n
+    const uint16_t* antilog; // [2^m]: alpha^i for i <= 2^m - 1
+    const uint16_t* log;     // [2^m]
+    int cw_stride, msg_stride; // bytes between consecutive frames
+};
+constexpr int kBchWarpsPerBlock = 8;
+cudaError_t bch_launch(const BchLaunch& p, cudaStream_t stream);
+
+struct DemapLaunch {
+    const float* iq; // [frames][n_syms][2]
+    const float* n0; // [frames]
+    int8_t* llr;     // [frames][N]
+    int frames, n_syms;
+    int constellation; // 0 QPSK, 4 8PSK
+    int row0, row1, row2; // 8PSK deinterleaver row offsets
+};
+cudaError_t demap_launch(const DemapLaunch& p, cudaStream_t stream);
+
+} // namespace dvbs2b200

@@ -1,0 +1,259 @@
+"""dvbs2rx_b200 -- ctypes binding of libdvbs2_b200.so (C ABI in include/dvbs2_b200.h).
+
+Host side of the B200 DVB-S2 FEC decode path.  The enum ordinals and block-level names mirror
+gr-dvbs2rx (include/gnuradio/dvbs2rx/dvb_config.h:15-121, python/dvbs2rx/params.py).  There is
+no CPU fallback: compute calls raise Dvbs2Error when the CUDA library or a device is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libdvbs2_b200.so")
+
+# ---- enums (dvb_config.h) -----------------------------------------------------------------------
+STANDARD_DVBS2, STANDARD_DVBT2 = 0, 1
+FECFRAME_SHORT, FECFRAME_NORMAL, FECFRAME_MEDIUM = 0, 1, 2
+OM_CODEWORD, OM_MESSAGE = 0, 1
+INFO_OFF, INFO_ON = 0, 1
+_RATES = ("C1_4 C1_3 C2_5 C1_2 C3_5 C2_3 C3_4 C4_5 C5_6 C7_8 C8_9 C9_10 C13_45 C9_20 C90_180 C96_180 "
+          "C11_20 C100_180 C104_180 C26_45 C18_30 C28_45 C23_36 C116_180 C20_30 C124_180 C25_36 "
+          "C128_180 C13_18 C132_180 C22_30 C135_180 C140_180 C7_9 C154_180 C11_45 C4_15 C14_45 C7_15 "
+          "C8_15 C32_45 C2_9_VLSNR C1_5_MEDIUM C11_45_MEDIUM C1_3_MEDIUM C1_5_VLSNR_SF2 "
+          "C11_45_VLSNR_SF2 C1_5_VLSNR C4_15_VLSNR C1_3_VLSNR C_OTHER").split()
+RATE = {name: i for i, name in enumerate(_RATES)}
+globals().update(RATE)
+_MODS = ("MOD_QPSK MOD_16QAM MOD_64QAM MOD_256QAM MOD_8PSK MOD_8APSK MOD_16APSK MOD_8_8APSK "
+         "MOD_32APSK MOD_4_12_16APSK MOD_4_8_4_16APSK MOD_64APSK MOD_8_16_20_20APSK "
+         "MOD_4_12_20_28APSK MOD_128APSK MOD_256APSK MOD_BPSK MOD_BPSK_SF2 MOD_8VSB MOD_OTHER").split()
+MOD = {name: i for i, name in enumerate(_MODS)}
+globals().update(MOD)
+
+OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = 0, -1, -2, -3, -4
+TERM_PER_FRAME = 0
+
+
+class Dvbs2Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("dvbs2b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class CodeInfo(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("table", "n_ldpc", "k_ldpc", "q", "n_circ", "links_total",
+                                       "max_cn_deg", "kbch", "nbch", "t", "gf_m")]
+
+
+_lib = None
+
+# every symbol include/dvbs2_b200.h declares: (restype, argtypes)
+_P = C.c_void_p
+_SIGS = {
+    "dvbs2b200_version": (C.c_int, []),
+    "dvbs2b200_last_error": (C.c_char_p, []),
+    "dvbs2b200_device_count": (C.c_int, []),
+    "dvbs2b200_num_tables": (C.c_int, []),
+    "dvbs2b200_table_name": (C.c_char_p, [C.c_int]),
+    "dvbs2b200_lookup": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(CodeInfo)]),
+    "dvbs2b200_table_circulants": (C.c_int, [C.c_int, _P, C.c_int]),
+    "dvbs2b200_bch_genpoly": (C.c_int, [C.c_int, C.c_int, _P, C.c_int]),
+    "dvbs2b200_schedule_stats": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "dvbs2b200_code_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int]),
+    "dvbs2b200_code_export_tables": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "dvbs2b200_code_create_from_tables": (C.c_int, [C.POINTER(_P), C.c_int, _P, C.c_size_t]),
+    "dvbs2b200_code_destroy": (None, [_P]),
+    "dvbs2b200_code_info_get": (C.c_int, [_P, C.POINTER(CodeInfo)]),
+    "dvbs2b200_launch_count": (C.c_uint64, [_P]),
+    "dvbs2b200_ldpc_decode": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "dvbs2b200_ldpc_decode_dev": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "dvbs2b200_bch_decode": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "dvbs2b200_bch_decode_dev": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
+    "dvbs2b200_demap": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P]),
+    "dvbs2b200_demap_dev": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, _P]),
+    "dvbs2b200_fec_decode": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "dvbs2b200_fec_decode_dev": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+}
+EXPORTED_SYMBOLS = tuple(sorted(_SIGS))
+
+
+def lib():
+    """Load libdvbs2_b200.so (built by __graft_entry__.build()).  Fails loudly if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Dvbs2Error(ECUDA, "%s not built: run `python __graft_entry__.py build`" % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise Dvbs2Error(rc, lib().dvbs2b200_last_error().decode())
+
+
+def device_count():
+    return lib().dvbs2b200_device_count()
+
+
+def lookup(standard, framesize, rate):
+    info = CodeInfo()
+    _check(lib().dvbs2b200_lookup(standard, framesize, rate, C.byref(info)))
+    return info
+
+
+def table_circulants(table):
+    """(layer, group, shift) int arrays of one LDPC table."""
+    n = lib().dvbs2b200_table_circulants(table, None, 0)
+    if n < 0:
+        _check(n)
+    w = np.zeros(n, dtype=np.uint32)
+    lib().dvbs2b200_table_circulants(table, w.ctypes.data, n)
+    return (w >> 17).astype(np.int64), ((w >> 9) & 0xff).astype(np.int64), (w & 0x1ff).astype(np.int64)
+
+
+def bch_genpoly(framesize, t):
+    g = np.zeros(256, dtype=np.uint8)
+    deg = lib().dvbs2b200_bch_genpoly(framesize, t, g.ctypes.data, 256)
+    if deg < 0:
+        _check(deg)
+    return g[:deg + 1].copy()
+
+
+def schedule_stats(table):
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    _check(lib().dvbs2b200_schedule_stats(table, C.byref(a), C.byref(b), C.byref(c)))
+    return dict(steps_per_iter=a.value, max_depth=b.value, conflict_layers=c.value)
+
+
+def bits_per_symbol(constellation):
+    return {MOD_QPSK: 2, MOD_8PSK: 3}.get(constellation, 0)  # noqa: F821
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _np(a, dtype):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a
+
+
+class Code:
+    """One (standard, framesize, rate) bound to one CUDA device -- the state a gr-dvbs2rx block
+    instance holds (ldpc_decoder_bb_impl.cc:79-368, bch_decoder_bb_impl.cc:43-71)."""
+
+    def __init__(self, standard=STANDARD_DVBS2, framesize=FECFRAME_NORMAL, rate=None, device=0, tables=None):
+        self._h = _P()
+        if tables is not None:
+            buf = np.ascontiguousarray(tables, dtype=np.uint8)
+            _check(lib().dvbs2b200_code_create_from_tables(C.byref(self._h), device, buf.ctypes.data, buf.size))
+        else:
+            _check(lib().dvbs2b200_code_create(C.byref(self._h), device, standard, framesize, rate))
+        self.info = CodeInfo()
+        _check(lib().dvbs2b200_code_info_get(self._h, C.byref(self.info)))
+        self.device = device
+        self.N = self.info.n_ldpc
+        self.kbch, self.nbch = self.info.kbch, self.info.nbch
+
+    def close(self):
+        if self._h:
+            lib().dvbs2b200_code_destroy(self._h)
+            self._h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(lib().dvbs2b200_launch_count(self._h))
+
+    def export_tables(self):
+        size = C.c_size_t()
+        _check(lib().dvbs2b200_code_export_tables(self._h, None, 0, C.byref(size)))
+        buf = np.zeros(size.value, dtype=np.uint8)
+        _check(lib().dvbs2b200_code_export_tables(self._h, buf.ctypes.data, buf.size, C.byref(size)))
+        return buf
+
+    def out_bytes(self, output_mode):
+        return (self.nbch if output_mode else self.N) // 8
+
+    # ---- host-buffer entry points (numpy) ------------------------------------------------------
+    def ldpc_decode(self, llr, max_trials=25, term_group=TERM_PER_FRAME, output_mode=OM_MESSAGE,
+                    want_post=False, want_trials=True):
+        llr = _np(llr, np.int8).reshape(-1, self.N)
+        F = llr.shape[0]
+        hard = np.empty((F, self.out_bytes(output_mode)), dtype=np.uint8)
+        post = np.empty((F, self.N), dtype=np.int8) if want_post else None
+        trials = np.empty(F, dtype=np.int32) if want_trials else None
+        _check(lib().dvbs2b200_ldpc_decode(self._h, llr.ctypes.data, F, max_trials, term_group, output_mode,
+                                           hard.ctypes.data, _ptr(post), _ptr(trials)))
+        return hard, post, trials
+
+    def bch_decode(self, cw):
+        cw = _np(cw, np.uint8).reshape(-1, self.nbch // 8)
+        F = cw.shape[0]
+        msg = np.empty((F, self.kbch // 8), dtype=np.uint8)
+        corr = np.empty(F, dtype=np.int32)
+        _check(lib().dvbs2b200_bch_decode(self._h, cw.ctypes.data, F, msg.ctypes.data, corr.ctypes.data))
+        return msg, corr
+
+    def demap(self, constellation, iq, n0):
+        bits = bits_per_symbol(constellation)
+        if not bits:
+            raise Dvbs2Error(EUNSUPPORTED, "Unsupported constellation")
+        iq = _np(iq, np.float32).reshape(-1, self.N // bits, 2)
+        F = iq.shape[0]
+        n0 = _np(np.broadcast_to(np.asarray(n0, dtype=np.float32), (F,)), np.float32)
+        llr = np.empty((F, self.N), dtype=np.int8)
+        _check(lib().dvbs2b200_demap(self._h, constellation, iq.ctypes.data, F, n0.ctypes.data, llr.ctypes.data))
+        return llr
+
+    def fec_decode(self, llr=None, iq=None, n0=None, constellation=0, max_trials=25, term_group=TERM_PER_FRAME):
+        if iq is not None:
+            bits = bits_per_symbol(constellation)
+            iq = _np(iq, np.float32).reshape(-1, self.N // bits, 2)
+            F = iq.shape[0]
+            n0 = _np(np.broadcast_to(np.asarray(n0, dtype=np.float32), (F,)), np.float32)
+        else:
+            llr = _np(llr, np.int8).reshape(-1, self.N)
+            F = llr.shape[0]
+        msg = np.empty((F, self.kbch // 8), dtype=np.uint8)
+        trials = np.empty(F, dtype=np.int32)
+        corr = np.empty(F, dtype=np.int32)
+        _check(lib().dvbs2b200_fec_decode(self._h, constellation, _ptr(iq), _ptr(n0), _ptr(llr), F, max_trials,
+                                          term_group, msg.ctypes.data, trials.ctypes.data, corr.ctypes.data))
+        return msg, trials, corr
+
+    # ---- raw-pointer entry points (device or pinned host addresses as ints) ----------------------
+    def ldpc_decode_ptr(self, llr_ptr, frames, max_trials, term_group, output_mode, hard_ptr, post_ptr, trials_ptr):
+        _check(lib().dvbs2b200_ldpc_decode(self._h, llr_ptr, frames, max_trials, term_group, output_mode,
+                                           hard_ptr, post_ptr, trials_ptr))
+
+    def fec_decode_ptr(self, constellation, iq_ptr, n0_ptr, llr_ptr, frames, max_trials, term_group, msg_ptr,
+                       trials_ptr, corr_ptr):
+        _check(lib().dvbs2b200_fec_decode(self._h, constellation, iq_ptr, n0_ptr, llr_ptr, frames, max_trials,
+                                          term_group, msg_ptr, trials_ptr, corr_ptr))
+
+    def ldpc_decode_dev(self, d_llr, frames, max_trials, term_group, output_mode, d_hard, d_post, d_trials, stream):
+        _check(lib().dvbs2b200_ldpc_decode_dev(self._h, d_llr, frames, max_trials, term_group, output_mode,
+                                               d_hard, d_post, d_trials, stream))
+
+    def bch_decode_dev(self, d_cw, frames, d_msg, d_corr, stream):
+        _check(lib().dvbs2b200_bch_decode_dev(self._h, d_cw, frames, d_msg, d_corr, stream))
+
+    def demap_dev(self, constellation, d_iq, frames, d_n0, d_llr, stream):
+        _check(lib().dvbs2b200_demap_dev(self._h, constellation, d_iq, frames, d_n0, d_llr, stream))
+
+    def fec_decode_dev(self, constellation, d_iq, d_n0, d_llr, frames, max_trials, term_group, d_msg, d_trials,
+                       d_corr, stream):
+        _check(lib().dvbs2b200_fec_decode_dev(self._h, constellation, d_iq, d_n0, d_llr, frames, max_trials,
+                                              term_group, d_msg, d_trials, d_corr, stream))

@@ -1,0 +1,157 @@
+/*
+ * dvbs2_b200.h -- C ABI of libdvbs2_b200.so: the B200 (sm_100a) DVB-S2 FEC decode path
+ * (soft demap -> layered offset-min-sum LDPC -> BCH) that drops in behind gr-dvbs2rx's
+ * xfecframe_demapper_cb / ldpc_decoder_bb / bch_decoder_bb blocks.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns 0 (DVBS2B200_OK) or a negative
+ *     DVBS2B200_E*; nothing throws, nothing prints.  dvbs2b200_last_error() gives the text.
+ *   - enum ordinals (standard, framesize, rate, constellation, output mode) are the
+ *     reference's: include/gnuradio/dvbs2rx/dvb_config.h:15-121.
+ *   - bit order is MSB first inside a byte, frames are contiguous
+ *     (lib/ldpc_decoder_bb_impl.cc:432-442, lib/bch.cc:436-450).
+ *   - a handle is bound to one CUDA device and one code (the reference is CCM: one MODCOD
+ *     per block instance) and is used by one host thread at a time (GNU Radio calls
+ *     general_work from one thread per block).
+ *   - "host" entry points take host pointers (pageable or pinned) and stage through pinned
+ *     buffers + the handle's stream; "_dev" entry points take device pointers and a
+ *     cudaStream_t (as void*) and are asynchronous on that stream.
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry point
+ *     fails with DVBS2B200_ECUDA.
+ *
+ * Reference interfaces replaced (file:line under the reference checkout):
+ *   dvbs2b200_ldpc_decode   <- int (*decode)(void*, int8_t*, int)   lib/ldpc_decoder_bb_impl.h:41,
+ *                              ldpc_<isa>::ldpc_dec_decode           lib/ldpc_decoder_bb_impl.cc:34-52,
+ *                              + hard decision / packing loop        lib/ldpc_decoder_bb_impl.cc:406-447
+ *   dvbs2b200_code_create   <- ldpc_<isa>::ldpc_dec_init + table/ISA dispatch
+ *                                                                    lib/ldpc_decoder_bb_impl.cc:97-350,
+ *                              galois_field / bch_codec construction lib/bch_decoder_bb_impl.cc:56-70
+ *   dvbs2b200_bch_decode    <- d_codec->decode(in, out)              lib/bch_decoder_bb_impl.cc:94-111
+ *                              (bch_codec::decode(u8)                lib/bch.cc:467-487)
+ *   dvbs2b200_demap         <- d_qpsk->demap_soft / d_mod->soft + deinterleave
+ *                                                                    lib/xfecframe_demapper_cb_impl.cc:151-176
+ *   dvbs2b200_fec_decode    <- the three general_work bodies chained (demapper -> LDPC -> BCH)
+ *   dvbs2b200_lookup        <- get_fec_info                          lib/fec_params.cc:16-344
+ */
+#ifndef DVBS2_B200_H
+#define DVBS2_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVBS2B200_VERSION 100 /* 0.1.0 */
+
+enum {
+    DVBS2B200_OK = 0,
+    DVBS2B200_EINVAL = -1,       /* bad argument */
+    DVBS2B200_EUNSUPPORTED = -2, /* code / constellation not supported (yet) */
+    DVBS2B200_ECUDA = -3,        /* no device, launch or runtime failure */
+    DVBS2B200_ENOMEM = -4
+};
+
+/* termination coupling of the LDPC iteration loop */
+enum {
+    DVBS2B200_TERM_PER_FRAME = 0 /* each frame stops when ITS syndrome is clean */
+    /* 16 or 32: the reference's SIMD-batch semantics (lib/ldpc_decoder/layered_decoder.hh:153):
+     * a group of that many consecutive frames iterates until all of them are clean. */
+};
+
+typedef struct dvbs2b200_code dvbs2b200_code; /* opaque */
+
+typedef struct {
+    int table;      /* index into the LDPC table list, dvbs2b200_table_name(table) */
+    int n_ldpc;     /* LDPC codeword bits (16200 / 32400 / 64800) */
+    int k_ldpc;     /* LDPC information bits of the table */
+    int q;          /* (n_ldpc - k_ldpc) / 360 = number of layers */
+    int n_circ;     /* 360x360 circulants in the data part */
+    int links_total;
+    int max_cn_deg;
+    int kbch, nbch, t; /* lib/fec_params.cc; kldpc used for OM_MESSAGE output is nbch */
+    int gf_m;          /* 16 normal, 14 short, 15 medium (lib/bch_decoder_bb_impl.cc:58-63) */
+} dvbs2b200_code_info;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int dvbs2b200_version(void);
+const char* dvbs2b200_last_error(void); /* thread-local, never NULL */
+int dvbs2b200_device_count(void);       /* >= 0, or DVBS2B200_ECUDA */
+
+/* ---- code parameters (pure host functions, usable without a GPU) -------------------------- */
+int dvbs2b200_num_tables(void);
+const char* dvbs2b200_table_name(int table);
+int dvbs2b200_lookup(int standard, int framesize, int rate, dvbs2b200_code_info* info);
+/* circulant list of a table: word = layer << 17 | group << 9 | shift; returns the count */
+int dvbs2b200_table_circulants(int table, uint32_t* out, int cap);
+/* BCH generator polynomial of a code, g[i] = coefficient of x^i; returns its degree */
+int dvbs2b200_bch_genpoly(int framesize, int t, uint8_t* g, int cap);
+/* per-layer serial-order schedule statistics (wavefront steps per iteration, deepest layer) */
+int dvbs2b200_schedule_stats(int table, int* steps_per_iter, int* max_depth, int* conflict_layers);
+
+/* ---- handles ------------------------------------------------------------------------------ */
+/* Builds the packed code tables on the host (circulants, serial-order schedule, GF log/antilog,
+ * generator data), uploads them to `device`, creates the stream and staging buffers. */
+int dvbs2b200_code_create(dvbs2b200_code** h, int device, int standard, int framesize, int rate);
+/* The packed tables as one relocatable blob, so that rank 0 can build them once and
+ * broadcast them (one ncclBroadcast through torch.distributed) to the other ranks. */
+int dvbs2b200_code_export_tables(const dvbs2b200_code* h, void* buf, size_t cap, size_t* size);
+int dvbs2b200_code_create_from_tables(dvbs2b200_code** h, int device, const void* blob, size_t size);
+void dvbs2b200_code_destroy(dvbs2b200_code* h);
+int dvbs2b200_code_info_get(const dvbs2b200_code* h, dvbs2b200_code_info* info);
+/* number of kernel launches issued through this handle so far (bench.py's gpu_launches) */
+uint64_t dvbs2b200_launch_count(const dvbs2b200_code* h);
+
+/* ---- LDPC --------------------------------------------------------------------------------- */
+/* llr        [frames][n_ldpc] int8, frame-major (the block's input stream)
+ * max_trials 0 -> 25 (lib/ldpc_decoder_bb_impl.cc:391,402)
+ * term_group DVBS2B200_TERM_PER_FRAME, or 16 / 32 for the reference's batch-coupled loop
+ *            (frames must then be a multiple of term_group)
+ * output_mode OM_CODEWORD = 0 -> n_ldpc/8 bytes per frame, OM_MESSAGE = 1 -> nbch/8 bytes
+ * hard       [frames][bytes] packed hard decisions (llr < 0 -> 1), MSB first
+ * llr_post   NULL or [frames][n_ldpc] posterior LLRs (what the reference leaves in `code`
+ *            and publishes on "llr_pdu")
+ * trials_left NULL or [frames]: the reference's return value (>= 0 trials left, -1 = not
+ *            converged); in group mode every frame of a group reports the group's value. */
+int dvbs2b200_ldpc_decode(dvbs2b200_code* h, const int8_t* llr, int frames, int max_trials,
+                          int term_group, int output_mode, uint8_t* hard, int8_t* llr_post,
+                          int32_t* trials_left);
+int dvbs2b200_ldpc_decode_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
+                              int term_group, int output_mode, uint8_t* d_hard,
+                              int8_t* d_llr_post, int32_t* d_trials_left, void* stream);
+
+/* ---- BCH ---------------------------------------------------------------------------------- */
+/* cw [frames][nbch/8] -> msg [frames][kbch/8]; corrections[f] = #bits corrected, 0, or -1
+ * (uncorrectable; the roots that were found are still flipped, lib/bch.cc:476-483). */
+int dvbs2b200_bch_decode(dvbs2b200_code* h, const uint8_t* cw, int frames, uint8_t* msg,
+                         int32_t* corrections);
+int dvbs2b200_bch_decode_dev(dvbs2b200_code* h, const uint8_t* d_cw, int frames, uint8_t* d_msg,
+                             int32_t* d_corrections, void* stream);
+
+/* ---- soft demapper ------------------------------------------------------------------------ */
+/* iq [frames][n_ldpc/bits][2] float (XFECFRAME symbols, pilots already removed)
+ * n0 [frames] noise variance per frame -- explicit, the library has no hidden SNR feedback
+ * llr [frames][n_ldpc] int8, deinterleaved to codeword order.
+ * constellation: MOD_QPSK (0) or MOD_8PSK (4); others -> DVBS2B200_EUNSUPPORTED, as the
+ * reference throws "Unsupported constellation" (lib/xfecframe_demapper_cb_impl.cc:70-72). */
+int dvbs2b200_demap(dvbs2b200_code* h, int constellation, const float* iq, int frames,
+                    const float* n0, int8_t* llr);
+int dvbs2b200_demap_dev(dvbs2b200_code* h, int constellation, const float* d_iq, int frames,
+                        const float* d_n0, int8_t* d_llr, void* stream);
+
+/* ---- fused chain: LLRs (or symbols) in, BBFRAME bytes out ---------------------------------- */
+/* Runs [demap ->] LDPC (OM_MESSAGE) -> BCH with intermediates kept in device memory.
+ * iq == NULL: start from llr.  msg [frames][kbch/8]; status arrays may be NULL. */
+int dvbs2b200_fec_decode(dvbs2b200_code* h, int constellation, const float* iq, const float* n0,
+                         const int8_t* llr, int frames, int max_trials, int term_group,
+                         uint8_t* msg, int32_t* trials_left, int32_t* corrections);
+int dvbs2b200_fec_decode_dev(dvbs2b200_code* h, int constellation, const float* d_iq,
+                             const float* d_n0, const int8_t* d_llr, int frames, int max_trials,
+                             int term_group, uint8_t* d_msg, int32_t* d_trials_left,
+                             int32_t* d_corrections, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVBS2_B200_H */
