@@ -230,7 +230,6 @@ template <int CNT_MAX, int MSG_WORDS>
 __global__ void __launch_bounds__(kLdpcThreads, 1) ldpc_decode_kernel(const LdpcLaunch p)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    int8_t* L = reinterpret_cast<int8_t*>(smem);
     uint32_t* msg = reinterpret_cast<uint32_t*>(smem + p.smem_msg_off);
     const uint4* layers = reinterpret_cast<const uint4*>(smem + p.smem_tab_off);
     const uint32_t* edges = reinterpret_cast<const uint32_t*>(smem + p.smem_tab_off + (size_t)p.q * 16);
@@ -258,14 +257,16 @@ __global__ void __launch_bounds__(kLdpcThreads, 1) ldpc_decode_kernel(const Ldpc
     for (int f = blockIdx.x; f < p.frames; f += gridDim.x) {
         // ---- soft input: HBM -> shared memory ----------------------------------------------
         const int8_t* src = p.llr + (size_t)f * N;
+        // bulk copies need 16-byte aligned addresses and sizes on both sides: place the frame in
+        // shared memory with the same misalignment as its global address (16 spare bytes are
+        // reserved) and peel the unaligned head / tail with plain loads.
+        const uint32_t mis = (uint32_t)((uintptr_t)src & 15u);
+        int8_t* const L = reinterpret_cast<int8_t*>(smem) + mis;
         {
-            // bulk copies need 16-byte aligned addresses and sizes; peel an unaligned head/tail
-            const uint32_t mis = (uint32_t)((uintptr_t)src & 15u);
             const uint32_t head = mis ? (16u - mis) : 0u;
             const uint32_t body = ((uint32_t)N - head) & ~15u;
             const uint32_t tail = (uint32_t)N - head - body;
             if (tid == 0) {
-                fence_proxy_async();
                 mbar_expect_tx(bar, body);
                 tma_load_1d(L + head, src + head, body, bar);
             }
@@ -344,17 +345,27 @@ __global__ void __launch_bounds__(kLdpcThreads, 1) ldpc_decode_kernel(const Ldpc
         if (p.hard) {
             // llr < 0 -> 1, MSB first: lib/ldpc_decoder_bb_impl.cc:432-442
             uint8_t* dst = p.hard + (size_t)f * p.out_bytes;
-            const uint2* L8 = reinterpret_cast<const uint2*>(L);
-            for (int b = tid; b < p.out_bytes; b += kLdpcThreads) {
-                const uint2 w = L8[b];
-                const uint32_t hi4 = ((((w.x >> 7) & 0x01010101u) * 0x08040201u) >> 24) & 0xFu;
-                const uint32_t lo4 = ((((w.y >> 7) & 0x01010101u) * 0x08040201u) >> 24) & 0xFu;
-                dst[b] = (uint8_t)((hi4 << 4) | lo4);
+            if ((mis & 7u) == 0) {
+                const uint2* L8 = reinterpret_cast<const uint2*>(L);
+                for (int b = tid; b < p.out_bytes; b += kLdpcThreads) {
+                    const uint2 w = L8[b];
+                    const uint32_t hi4 = ((((w.x >> 7) & 0x01010101u) * 0x08040201u) >> 24) & 0xFu;
+                    const uint32_t lo4 = ((((w.y >> 7) & 0x01010101u) * 0x08040201u) >> 24) & 0xFu;
+                    dst[b] = (uint8_t)((hi4 << 4) | lo4);
+                }
+            } else {
+                for (int b = tid; b < p.out_bytes; b += kLdpcThreads) {
+                    uint32_t v = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        v |= (L[8 * b + k] < 0 ? 1u : 0u) << (7 - k);
+                    dst[b] = (uint8_t)v;
+                }
             }
         }
         if (p.llr_post) {
             int8_t* dst = p.llr_post + (size_t)f * N;
-            if ((((uintptr_t)dst) & 15u) == 0 && (N & 15) == 0) {
+            if ((((uintptr_t)dst) & 15u) == 0 && (N & 15) == 0 && mis == 0) {
                 if (tid == 0) {
                     tma_store_1d(dst, L, (uint32_t)N);
                     tma_store_commit();
@@ -388,7 +399,7 @@ cudaError_t launch_one(const LdpcLaunch& p, int grid, size_t smem, cudaStream_t 
 
 size_t ldpc_smem_bytes(int N, int R, int msg_words, uint32_t tab_bytes, LdpcLaunch* p)
 {
-    size_t off = ((size_t)N + 15) & ~(size_t)15;
+    size_t off = (((size_t)N + 15) & ~(size_t)15) + 16; // +16: frames keep their global misalignment
     if (p)
         p->smem_msg_off = (uint32_t)off;
     off += (size_t)R * msg_words * 4;
