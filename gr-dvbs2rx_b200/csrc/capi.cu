@@ -76,9 +76,10 @@ struct dvbs2b200_code {
     BlobHeader hdr;
     uint8_t* d_blob = nullptr;
     size_t ldpc_smem = 0;
+    int ldpc_ctas = 0; // resident LDPC CTAs per SM
     uint64_t launches = 0;
     // staging for the host-pointer entry points
-    DevBuf d_in, d_mid, d_out, d_post, d_i32a, d_i32b, d_n0, d_llr, d_sync;
+    DevBuf d_in, d_mid, d_out, d_post, d_i32a, d_i32b, d_n0, d_llr, d_sync, d_scratch;
 };
 
 namespace {
@@ -130,7 +131,9 @@ int create_from_blob(dvbs2b200_code** out, int device, std::vector<uint8_t>&& bl
         return bail(cuda_fail(e, "cudaMalloc(tables)"));
     if ((e = cudaMemcpy(h->d_blob, h->blob.data(), h->blob.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
         return bail(cuda_fail(e, "cudaMemcpy(tables)"));
-    h->ldpc_smem = ldpc_smem_bytes(h->hdr.N, h->hdr.R, h->hdr.msg_words, h->hdr.smem_bytes, nullptr);
+    h->ldpc_smem = ldpc_smem_bytes(h->hdr.N, h->hdr.smem_bytes, nullptr);
+    if (h->hdr.max_cnt <= 28 && h->ldpc_smem <= (size_t)h->smem_optin)
+        h->ldpc_ctas = ldpc_ctas_per_sm(h->hdr.max_cnt, h->hdr.msg_words == 2, h->ldpc_smem);
     *out = h;
     return DVBS2B200_OK;
 }
@@ -154,12 +157,13 @@ struct DeviceGuard {
 
 int ldpc_out_bytes(const BlobHeader& h, int output_mode) { return (output_mode ? h.kldpc_out : h.N) / 8; }
 
-// grid size: one persistent CTA per SM; in group mode a multiple of the group that fits the SMs
+// grid size: persistent CTAs, as many as are resident at once; in group mode a multiple of the group
 int ldpc_grid(const dvbs2b200_code* h, int frames, int group)
 {
-    int grid = std::min(frames, h->sm_count);
+    const int resident = h->sm_count * h->ldpc_ctas;
+    int grid = std::min(frames, resident);
     if (group > 1)
-        grid = std::min(frames, (h->sm_count / group) * group);
+        grid = std::min(frames, (resident / group) * group);
     return grid;
 }
 
@@ -177,14 +181,14 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
         return fail(DVBS2B200_EINVAL, "term_group must be 0, 16 or 32");
     if (term_group > 1 && frames % term_group)
         return fail(DVBS2B200_EINVAL, "frames must be a multiple of term_group");
-    if (term_group > 1 && h->sm_count < term_group)
-        return fail(DVBS2B200_EUNSUPPORTED, "device has fewer SMs than term_group");
-    if (h->ldpc_smem > (size_t)h->smem_optin)
-        return fail(DVBS2B200_EUNSUPPORTED,
-                    "this code needs more shared memory per CTA than the device offers (low-rate normal frames: "
-                    "packed 24-bit check-node state not built yet)");
     if (hd.max_cnt > 28)
         return fail(DVBS2B200_EUNSUPPORTED, "check-node degree above 30");
+    if (h->ldpc_ctas <= 0)
+        return fail(DVBS2B200_ECUDA, "LDPC kernel cannot be resident on this device (shared memory / registers)");
+    if (term_group > 1 && h->sm_count * h->ldpc_ctas < term_group)
+        return fail(DVBS2B200_EUNSUPPORTED, "device cannot hold term_group frames at once");
+    if (((uintptr_t)d_llr & 3) || ((uintptr_t)d_llr_post & 3))
+        return fail(DVBS2B200_EINVAL, "llr buffers must be 4-byte aligned");
     if (max_trials == 0)
         max_trials = 25; // lib/ldpc_decoder_bb_impl.cc:391,402
     LdpcLaunch p;
@@ -193,15 +197,24 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
     p.K = hd.K;
     p.R = hd.R;
     p.q = hd.q;
+    p.n_circ = hd.n_circ;
+    p.n_steps = hd.steps_per_iter;
     p.tab = h->d_blob + hd.smem_off;
     p.tab_bytes = hd.smem_bytes;
-    p.steps = reinterpret_cast<const StepRecDev*>(h->d_blob + hd.step_off);
-    p.order = reinterpret_cast<const uint16_t*>(h->d_blob + hd.order_off);
-    size_t smem = ldpc_smem_bytes(hd.N, hd.R, hd.msg_words, hd.smem_bytes, &p);
+    p.work = reinterpret_cast<const uint16_t*>(h->d_blob + hd.order_off);
+    size_t smem = ldpc_smem_bytes(hd.N, hd.smem_bytes, &p);
+    const int group = term_group > 1 ? term_group : 0;
+    const int grid = ldpc_grid(h, frames, group);
+    {
+        int rc = h->d_scratch.ensure((size_t)grid * hd.R * hd.msg_words * sizeof(uint32_t));
+        if (rc)
+            return rc;
+        p.msg_scratch = (uint32_t*)h->d_scratch.p;
+    }
     p.llr = d_llr;
     p.frames = frames;
     p.max_trials = max_trials;
-    p.group = term_group > 1 ? term_group : 0;
+    p.group = group;
     p.hard = d_hard;
     p.out_bytes = ldpc_out_bytes(hd, output_mode);
     p.llr_post = d_llr_post;
@@ -214,7 +227,7 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
         CU(cudaMemsetAsync(h->d_sync.p, 0, words * sizeof(unsigned), stream));
         p.gsync = (unsigned*)h->d_sync.p;
     }
-    cudaError_t e = ldpc_launch(p, hd.max_cnt, hd.msg_words, ldpc_grid(h, frames, p.group), smem, stream);
+    cudaError_t e = ldpc_launch(p, hd.max_cnt, hd.msg_words == 2, grid, smem, stream);
     if (e != cudaSuccess)
         return cuda_fail(e, "ldpc_launch");
     h->launches += 1;
@@ -431,7 +444,7 @@ void dvbs2b200_code_destroy(dvbs2b200_code* h)
     DeviceGuard g(h->device);
     if (h->stream)
         cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : { &h->d_in, &h->d_mid, &h->d_out, &h->d_post, &h->d_i32a, &h->d_i32b, &h->d_n0, &h->d_llr, &h->d_sync })
+    for (DevBuf* b : { &h->d_in, &h->d_mid, &h->d_out, &h->d_post, &h->d_i32a, &h->d_i32b, &h->d_n0, &h->d_llr, &h->d_sync, &h->d_scratch })
         b->release();
     if (h->d_blob)
         cudaFree(h->d_blob);

@@ -60,10 +60,13 @@ void build_schedule(const LdpcTableDef& def, Schedule& s)
             if (a && circ[a].first == circ[a - 1].first)
                 conflict = true; // sorted by group: equal neighbours share a group
         }
-        L.n_steps = 1;
-        L.step_begin = 0;
-        L.order_begin = 0;
+        L.conflict = conflict ? 1 : 0;
         if (!conflict) {
+            StepRec st;
+            st.layer = (uint16_t)i;
+            st.count = 0;
+            st.work_off = 0;
+            s.steps.push_back(st);
             s.steps_per_iter += 1;
             continue;
         }
@@ -81,19 +84,14 @@ void build_schedule(const LdpcTableDef& def, Schedule& s)
             level[j] = lv;
             depth = std::max(depth, lv);
         }
-        L.n_steps = (uint16_t)depth;
-        L.step_begin = (uint32_t)s.steps.size();
-        L.order_begin = (uint32_t)s.order.size();
-        uint16_t pos = 0;
         for (int lv = 1; lv <= depth; ++lv) {
             StepRec st;
-            st.begin = pos;
+            st.layer = (uint16_t)i;
+            st.work_off = (uint32_t)s.order.size();
             for (int j = 0; j < 360; ++j)
-                if (level[j] == lv) {
+                if (level[j] == lv)
                     s.order.push_back((uint16_t)j);
-                    ++pos;
-                }
-            st.count = (uint16_t)(pos - st.begin);
+            st.count = (uint16_t)(s.order.size() - st.work_off);
             s.steps.push_back(st);
         }
         s.steps_per_iter += depth;
@@ -234,11 +232,11 @@ bool build_blob(int standard, int framesize, int rate, std::vector<uint8_t>& blo
     h.layer_off = (uint32_t)off;
     off += sizeof(LayerRec) * s.layers.size();
     h.edge_off = (uint32_t)off;
-    off += sizeof(uint32_t) * s.edges.size();
+    off += sizeof(EdgeRec) * s.edges.size();
+    h.step_off = (uint32_t)off;
+    off += sizeof(StepRec) * s.steps.size();
     off = align16(off);
     h.smem_bytes = (uint32_t)(off - h.smem_off);
-    h.step_off = (uint32_t)off;
-    off = align16(off + sizeof(StepRec) * s.steps.size());
     h.order_off = (uint32_t)off;
     off = align16(off + sizeof(uint16_t) * s.order.size());
     std::vector<uint16_t> al, lg;
@@ -252,7 +250,7 @@ bool build_blob(int standard, int framesize, int rate, std::vector<uint8_t>& blo
     blob.assign(off, 0);
     memcpy(blob.data(), &h, sizeof(h));
     memcpy(blob.data() + h.layer_off, s.layers.data(), sizeof(LayerRec) * s.layers.size());
-    memcpy(blob.data() + h.edge_off, s.edges.data(), sizeof(uint32_t) * s.edges.size());
+    memcpy(blob.data() + h.edge_off, s.edges.data(), sizeof(EdgeRec) * s.edges.size());
     if (!s.steps.empty())
         memcpy(blob.data() + h.step_off, s.steps.data(), sizeof(StepRec) * s.steps.size());
     if (!s.order.empty())
@@ -282,7 +280,8 @@ bool validate_blob(const void* blob, size_t size, std::string& err)
     bool ok = h.q > 0 && h.q <= 180 && h.R == h.q * 360 && h.N == h.K + h.R && h.n_circ > 0 &&
               h.smem_off == sizeof(BlobHeader) && h.layer_off == h.smem_off &&
               h.edge_off == h.layer_off + sizeof(LayerRec) * (size_t)h.q &&
-              (size_t)h.smem_off + h.smem_bytes <= size && h.step_off <= size && h.order_off <= size &&
+              (size_t)h.smem_off + h.smem_bytes <= size && h.step_off <= h.smem_off + h.smem_bytes && h.order_off <= size &&
+              h.n_steps_total == h.steps_per_iter &&
               (size_t)h.antilog_off + gfn <= size && (size_t)h.log_off + gfn <= size &&
               (h.msg_words == 1 || h.msg_words == 2) && h.gf_m >= 14 && h.gf_m <= 16;
     if (!ok)

@@ -29,20 +29,26 @@ const ModcodDef* find_modcod(int standard, int framesize, int rate);
 
 // ---- packed blob ---------------------------------------------------------------------------
 constexpr uint32_t kBlobMagic = 0x32425344u; // "DSB2"
-constexpr uint32_t kBlobVersion = 3;
+constexpr uint32_t kBlobVersion = 4;
 
-// One per layer, 16 bytes, lives in shared memory.
+// One per layer, 8 bytes, lives in shared memory.
 struct LayerRec {
     uint32_t edge_begin; // first circulant of the layer in edges[]
     uint16_t cnt;        // data links per check node in this layer
-    uint16_t n_steps;    // 1 = no intra-layer conflict (identity order), else wavefront steps
-    uint32_t step_begin; // first entry in steps[] (conflict layers only)
-    uint32_t order_begin; // first entry in order[] (conflict layers only)
+    uint16_t conflict;   // 1 if two circulants of the layer share a 360-bit group
 };
-// One per wavefront step of a conflict layer (global memory).
+// One per circulant, 8 bytes, lives in shared memory (see pack_edge).
+struct EdgeRec {
+    uint32_t e0; // hi | a' << 17 | ra << 25
+    uint32_t e1; // PRMT selectors for p >= a': unpack | pack << 16
+};
+// One per schedule step of an iteration, 8 bytes, lives in shared memory.  A conflict-free layer
+// is one step (count == 0: check-node pair p = thread); a conflict layer is a run of wavefront
+// steps, each a list of `count` check-node indices j in work[work_off ...].
 struct StepRec {
-    uint16_t begin; // offset into the layer's 360-entry order[] slice
-    uint16_t count; // check nodes in this step
+    uint16_t layer;
+    uint16_t count;
+    uint32_t work_off;
 };
 
 struct BlobHeader {
@@ -56,18 +62,32 @@ struct BlobHeader {
     int32_t n_steps_total, n_conflict_layers;
     int32_t steps_per_iter, max_depth;
     // section offsets from the start of the blob, all 16-byte aligned
-    uint32_t smem_off, smem_bytes; // [LayerRec q][edges n_circ]: TMA-staged into shared memory
+    uint32_t smem_off, smem_bytes; // [LayerRec q][EdgeRec n_circ][StepRec steps_per_iter]: TMA-staged
     uint32_t layer_off, edge_off;  // (inside the smem section)
-    uint32_t step_off, order_off;  // StepRec[], uint16 order[]
+    uint32_t step_off, order_off;  // StepRec[] (inside the smem section), uint16 work[] (global)
     uint32_t antilog_off, log_off; // uint16[2^m] each: alpha^i (i < 2^m-1), log(x)
     uint32_t bch_shorten;          // s = 2^m - 1 - nbch
     uint32_t reserved1[5];
 };
 static_assert(sizeof(BlobHeader) % 16 == 0, "header must keep sections 16-byte aligned");
 
-// edge word in edges[]: hi | shift << 17, hi = group*360 + 360 - shift.
-// Check node j of the layer reads data bit  hi + j - (j >= shift ? 360 : 0).
-inline uint32_t pack_edge(int group, int shift) { return (uint32_t)(group * 360 + 360 - shift) | ((uint32_t)shift << 17); }
+// Shared-memory layout of a frame's posteriors ("pair-interleaved"): element m of 360-bit group g
+// sits at byte g*360 + 2*(m % 180) + m/180, parity bit c at K + 2*(c % (R/2)) + c/(R/2), so the
+// two check nodes p and p+180 of a layer always find their operands in ONE 16-bit word.
+// Check-node pair p reads, through circulant (group, shift = a' + 180*ra), the halfword at
+//   hi + 2p - (p >= a' ? 360 : 0),   hi = group*360 + 360 - 2a';
+// node p is the low byte iff (ra ^ (p < a')) == 0.
+inline EdgeRec pack_edge(int group, int shift)
+{
+    const int ap = shift % 180, ra = shift / 180;
+    EdgeRec e;
+    e.e0 = (uint32_t)(group * 360 + 360 - 2 * ap) | ((uint32_t)ap << 17) | ((uint32_t)ra << 25);
+    // PRMT selectors when p >= a' (r = ra); the kernel XORs 0x1111 / 0x0022 when p < a'
+    const uint32_t unpack = ra ? 0x8091u : 0x9180u; // bytes -> sign-extended s16x2 [node p | node p+180]
+    const uint32_t pack = ra ? 0x4402u : 0x4420u;   // s16x2 -> two bytes in memory order
+    e.e1 = unpack | (pack << 16);
+    return e;
+}
 
 // Builds the blob for a (standard, framesize, rate).  Returns false and sets err on failure.
 bool build_blob(int standard, int framesize, int rate, std::vector<uint8_t>& blob, std::string& err);
@@ -76,9 +96,9 @@ bool validate_blob(const void* blob, size_t size, std::string& err);
 // serial-order wavefront schedule of one table (also used for dvbs2b200_schedule_stats)
 struct Schedule {
     std::vector<LayerRec> layers;
-    std::vector<uint32_t> edges;
-    std::vector<StepRec> steps;
-    std::vector<uint16_t> order;
+    std::vector<EdgeRec> edges;
+    std::vector<StepRec> steps; // one iteration, in execution order
+    std::vector<uint16_t> order; // work[]: check-node indices of the conflict steps
     int max_cnt = 0, steps_per_iter = 0, max_depth = 0, conflict_layers = 0;
 };
 void build_schedule(const LdpcTableDef& def, Schedule& s);

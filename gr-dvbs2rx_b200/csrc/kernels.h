@@ -5,36 +5,36 @@
 
 namespace dvbs2b200 {
 
-constexpr int kLdpcThreads = 384; // 360 check nodes of a layer + 24 spare lanes = 12 warps
-
-struct StepRecDev {
-    uint16_t begin, count;
-};
+constexpr int kLdpcThreads = 192;  // 180 check-node pairs of a layer + 12 spare lanes = 6 warps
+constexpr int kLdpcCtasPerSm = 3;  // 3 x (N + tables) bytes of shared memory fit one SM
 
 struct LdpcLaunch {
     // code
-    int N, K, R, q;
-    const uint8_t* tab;  // device: [LayerRec q][edge words], 16-byte aligned
-    uint32_t tab_bytes;  // multiple of 16
-    const StepRecDev* steps;
-    const uint16_t* order;
+    int N, K, R, q, n_circ, n_steps;
+    const uint8_t* tab;   // device: [LayerRec q][EdgeRec n_circ][StepRec n_steps], 16-byte aligned
+    uint32_t tab_bytes;   // multiple of 16
+    const uint16_t* work; // check-node lists of the conflict steps
     // shared-memory carve-up (bytes from the start of dynamic shared memory)
-    uint32_t smem_msg_off, smem_tab_off, smem_bar_off;
+    uint32_t smem_tab_off, smem_bar_off;
+    // per-CTA check-node state, [grid][R * words] uint32, L2 resident
+    uint32_t* msg_scratch;
     // batch
-    const int8_t* llr; // [frames][N]
+    const int8_t* llr; // [frames][N], 4-byte aligned
     int frames;
     int max_trials;
-    int group;           // 0/1 per-frame termination, else frames per coupled group
+    int group;           // 0 per-frame termination, else frames per coupled group
     unsigned int* gsync; // [frames/group][max_trials + 2], zeroed (group mode only)
     uint8_t* hard;       // [frames][out_bytes] or null
     int out_bytes;
-    int8_t* llr_post;     // [frames][N] or null
+    int8_t* llr_post;     // [frames][N] or null, 4-byte aligned
     int32_t* trials_left; // [frames] or null
 };
 
 // fills the smem_* offsets of p (if non-null) and returns the dynamic shared memory size
-size_t ldpc_smem_bytes(int N, int R, int msg_words, uint32_t tab_bytes, LdpcLaunch* p);
-cudaError_t ldpc_launch(const LdpcLaunch& p, int max_cnt, int msg_words, int grid, size_t smem, cudaStream_t stream);
+size_t ldpc_smem_bytes(int N, uint32_t tab_bytes, LdpcLaunch* p);
+cudaError_t ldpc_launch(const LdpcLaunch& p, int max_cnt, bool wide, int grid, size_t smem, cudaStream_t stream);
+// resident CTAs per SM for this code's kernel instantiation (occupancy query)
+int ldpc_ctas_per_sm(int max_cnt, bool wide, size_t smem);
 
 struct BchLaunch {
     const uint8_t* cw; // [frames][n_bytes]

@@ -7,20 +7,26 @@
 //   lib/ldpc_decoder_bb_impl.cc:432-442         hard decision + MSB-first packing
 //
 // Design (B200-first, not a translation of the SIMD-across-frames CPU code):
-//   * one FECFRAME per CTA, persistent CTAs (one per SM) striding over the frames of a launch;
-//   * the frame's N int8 posteriors live in shared memory in codeword order for the whole
-//     decode; the soft input arrives with ONE bulk async copy (TMA, cp.async.bulk) per frame,
-//     HBM is touched again only to write the packed hard decisions (and, optionally, the
-//     posterior LLRs);
-//   * check->variable messages are never stored per edge: a check node's `deg` int8 messages
-//     are a function of {min0, min1, argmin, one sign bit per edge}, which is kept as one
-//     32-bit (deg <= 15) or 64-bit word per check node in shared memory -- lossless w.r.t.
-//     the reference's clamp-on-store, and what makes 64800 + 4*32400 bytes fit one SM;
-//   * the code's circulant table (layer records + edge words) is staged into shared memory
-//     with one TMA bulk copy per CTA;
-//   * one thread per check node of a layer (360 of the 384 threads); layers whose circulants
-//     share a 360-bit group are order sensitive in the reference (serial j), so they run as
-//     precomputed wavefront steps (code_tables.cc:build_schedule) -- same result, bit for bit.
+//   * one FECFRAME per CTA of 192 threads, three CTAs per SM, persistent over the batch;
+//   * the frame's N int8 posteriors stay in shared memory for the whole decode, in a
+//     "pair-interleaved" order (code_tables.h) chosen so that check nodes p and p+180 of a layer
+//     read/write ONE aligned 16-bit word per link: each thread runs TWO check nodes in the
+//     halves of a 32-bit register with the native s16x2 min/max/add instructions
+//     (VIMNMX.S16x2, VIADD.16x2) -- the 360-bit quasi-cyclic rotation costs one PRMT;
+//   * check->variable messages are never stored per edge.  A check node's `deg` int8 messages
+//     are a function of {min0, min1, argmin, one sign bit per link}: one 32-bit word (64-bit
+//     for deg > 15) per check node, lossless w.r.t. the reference's clamp-on-store.  These words
+//     live in a per-CTA global scratch that stays L2 resident (57 MB for 444 CTAs at rate 1/2),
+//     are read with one coalesced 8-byte load per thread per layer, prefetched a layer ahead;
+//   * HBM traffic is the compulsory one: the soft input is read once, the packed hard
+//     decisions (and optionally the posteriors) are written once;
+//   * the code's tables (layers, circulants with precomputed PRMT selectors, step list) are
+//     staged into shared memory with one TMA bulk copy per CTA;
+//   * layers whose circulants share a 360-bit group are order sensitive in the reference (it
+//     visits check nodes serially), so they run as precomputed wavefront steps of single check
+//     nodes (code_tables.cc:build_schedule) -- same result, bit for bit;
+//   * the syndrome test after an iteration is skipped when the check nodes of the final step,
+//     whose posteriors are final by then, already prove the frame is still bad.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -30,7 +36,7 @@ namespace dvbs2b200 {
 
 namespace {
 
-constexpr int kM = 360;
+constexpr int kPairs = 180; // check-node pairs per layer
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -64,241 +70,371 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-// TMA bulk copy shared -> global
-__device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_smem, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ int clamp8(int x) { return min(max(x, -128), 127); }
+// ---- s16x2 helpers: two check nodes per register ----------------------------------------------
+__device__ __forceinline__ uint32_t h2(int x) { return (uint32_t)(uint16_t)x * 0x00010001u; }
+__device__ __forceinline__ uint32_t vmin(uint32_t a, uint32_t b) { return __vmins2(a, b); }
+__device__ __forceinline__ uint32_t vmax(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+__device__ __forceinline__ uint32_t vadd(uint32_t a, uint32_t b) { return __vadd2(a, b); }
+__device__ __forceinline__ uint32_t vsub(uint32_t a, uint32_t b) { return __vsub2(a, b); }
+// PRMT with the full 4-bit selectors: bit 3 of a nibble replicates the selected byte's sign
+// (__byte_perm masks the selector with 0x7777, so it cannot express the sign-extending forms)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+// 0xFFFF in every half whose bit 15 is set
+__device__ __forceinline__ uint32_t signmask(uint32_t x) { return prmt(x, 0, 0xBB99); }
 
 struct LayerView {
     uint32_t edge_begin;
     int cnt;
-    int n_steps;
-    uint32_t step_begin;
-    uint32_t order_begin;
 };
-
-__device__ __forceinline__ LayerView load_layer(const uint4* layers, int i)
+__device__ __forceinline__ LayerView load_layer(const uint2* layers, int i)
 {
-    uint4 r = layers[i];
+    const uint2 r = layers[i];
     LayerView v;
     v.edge_begin = r.x;
     v.cnt = (int)(r.y & 0xffffu);
-    v.n_steps = (int)(r.y >> 16);
-    v.step_begin = r.z;
-    v.order_begin = r.w;
     return v;
 }
 
-// data-bit index read by check node j through edge word e (code_tables.h:pack_edge)
-__device__ __forceinline__ int edge_index(uint32_t e, int j)
-{
-    int a = (int)(e >> 17);
-    int idx = (int)(e & 0x1ffffu) + j;
-    return (j >= a) ? idx - kM : idx;
-}
+// byte address of element s of a 360-bit group / of parity bit c in the pair-interleaved layout
+__device__ __forceinline__ int data_addr(int group_base, int s) { return group_base + 2 * (s >= kPairs ? s - kPairs : s) + (s >= kPairs); }
+__device__ __forceinline__ int parity_addr(int K, int half, int c) { return K + 2 * (c >= half ? c - half : c) + (c >= half); }
 
-// Compressed check-node state.
-//   bits  0..5   min(min0, 32)     bits 6..11  min(min1, 32)     bits 12..16 argmin link
-//   MSG_WORDS == 1: sign bit of link d at bit 17 + d       (deg <= 15)
-//   MSG_WORDS == 2: sign bits in the second word            (deg <= 32)
-template <int MSG_WORDS>
-struct CnState {
-    uint32_t lo, hi;
-    __device__ __forceinline__ uint32_t signs() const { return MSG_WORDS == 1 ? (lo >> 17) : hi; }
-};
+// Compressed check-node state word.
+//   bits 0..5 min(min0, 32)   bits 6..11 min(min1, 32)   bits 12..16 argmin link
+//   !WIDE: sign bit of link d at bit 17 + d (deg <= 15);  WIDE: sign bits in a second word.
+// Links: 0 = own parity bit, 1 = previous parity bit of the zig-zag, 2.. = data bits.
 
-template <int MSG_WORDS>
-__device__ __forceinline__ CnState<MSG_WORDS> load_state(const uint32_t* msg, int cn)
-{
-    CnState<MSG_WORDS> s;
-    if (MSG_WORDS == 1) {
-        s.lo = msg[cn];
-        s.hi = 0;
-    } else {
-        uint2 w = reinterpret_cast<const uint2*>(msg)[cn];
-        s.lo = w.x;
-        s.hi = w.y;
-    }
-    return s;
-}
-
-// One check-node update: lib/ldpc_decoder/layered_decoder.hh:57-76 + algorithms.hh:170-206.
-// Link order inside a check node is irrelevant to the result (min0/min1/sign-xor are
-// symmetric; a tie on the minimum gives min1 == min0), so parity links come first here.
-template <int CNT_MAX, int MSG_WORDS>
-__device__ __forceinline__ void process_cn(int8_t* __restrict__ L, uint32_t* __restrict__ msg, const uint32_t* __restrict__ edges,
-                                           const LayerView& lv, int layer, int j, int K, int q)
+// ---- two check nodes (p, p + 180) of a conflict-free layer ---------------------------------------
+// lib/ldpc_decoder/layered_decoder.hh:57-76 + algorithms.hh:170-206, both nodes at once.
+template <int CNT_MAX, bool WIDE, bool SELF_CHECK>
+__device__ __forceinline__ int process_pair(int8_t* __restrict__ L, const uint2* __restrict__ edges, const LayerView& lv, int layer,
+                                            int p, int K, int q, uint32_t wA, uint32_t wB, uint32_t sA, uint32_t sB,
+                                            uint32_t* __restrict__ msg_out)
 {
     constexpr int DEG_MAX = CNT_MAX + 2;
-    const int cn = kM * layer + j;
-    const int c = q * j + layer; // parity bit of this check in codeword order
-    const CnState<MSG_WORDS> st = load_state<MSG_WORDS>(msg, cn);
-    const int old_min0 = (int)(st.lo & 63u);
-    const int old_min1 = (int)((st.lo >> 6) & 63u);
-    const int old_arg = (int)((st.lo >> 12) & 31u);
-    const uint32_t old_signs = st.signs();
+    const bool first = (layer == 0 && p == 0); // check 0 has no previous parity link; check 180*q does
+    const int half = kPairs * q;
+    // ---- decode the stored state into s16x2 ----
+    const uint32_t m0 = (wA & 63u) | ((wB & 63u) << 16);
+    const uint32_t m1 = ((wA >> 6) & 63u) | (((wB >> 6) & 63u) << 16);
+    const uint32_t x01 = m0 ^ m1;
+    const uint32_t argA = (wA >> 12) & 31u, argB = (wB >> 12) & 31u;
+    // one-hot argmin and inverted sign bits: link d of node A at bit d, of node B at bit 16 + d
+    uint32_t hot_lo, hot_hi = 0, nsg_lo, nsg_hi = 0;
+    if (!WIDE) {
+        hot_lo = (1u << argA) | (0x10000u << argB);
+        nsg_lo = ~((wA >> 17) | ((wB >> 17) << 16));
+    } else {
+        hot_lo = ((1u << argA) & 0xffffu) | (((1u << argB) & 0xffffu) << 16);
+        hot_hi = ((1u << argA) >> 16) | ((1u << argB) & 0xffff0000u);
+        nsg_lo = ~((sA & 0xffffu) | (sB << 16));
+        nsg_hi = ~((sA >> 16) | (sB & 0xffff0000u));
+    }
 
     int adr[DEG_MAX];
-    int v[DEG_MAX];
-    // link 0: own parity bit; link 1: previous parity bit of the zig-zag (absent for check 0)
-    adr[0] = K + c;
-    adr[1] = K + c - 1;
-    const bool has_prev = (c > 0);
+    uint32_t sel[DEG_MAX];
+    uint32_t v[DEG_MAX], mag[DEG_MAX];
+    const int c = q * p + layer;
+    adr[0] = K + 2 * c;
+    sel[0] = 0x9180u | (0x4420u << 16);
+    // the word of parity bit 180q - 1 holds node B's previous parity bit in its LOW byte
+    adr[1] = first ? K + 2 * (half - 1) : K + 2 * c - 2;
+    sel[1] = first ? (0x8091u | (0x4402u << 16)) : sel[0];
 #pragma unroll
-    for (int d = 0; d < CNT_MAX; ++d)
-        adr[d + 2] = (d < lv.cnt) ? edge_index(edges[lv.edge_begin + d], j) : 0;
+    for (int d = 0; d < CNT_MAX; ++d) {
+        if (d < lv.cnt) {
+            const uint2 e = edges[lv.edge_begin + d];
+            const int ap = (int)((e.x >> 17) & 0xffu);
+            const bool lt = p < ap;
+            adr[d + 2] = (int)(e.x & 0x1ffffu) + 2 * p - (lt ? 0 : 360);
+            sel[d + 2] = lt ? (e.y ^ 0x00221111u) : e.y;
+        } else {
+            adr[d + 2] = 0;
+            sel[d + 2] = 0;
+        }
+    }
 
-    int min0 = 127, min1 = 127, arg = 0;
-    int sx = 0;
+    uint32_t k0 = h2(0x7fff), k1 = h2(0x7fff), sx = 0;
+#pragma unroll
+    for (int d = 0; d < DEG_MAX; ++d) {
+        const bool live = (d < 2) || (d - 2 < lv.cnt);
+        if (live) {
+            const uint32_t raw = *reinterpret_cast<const uint16_t*>(L + adr[d]);
+            const uint32_t l = prmt(raw, 0, sel[d] & 0xffffu);
+            // stored message: +-(d == argmin ? min1 : min0), clamped to [-32, 31]
+            const uint32_t hot = (!WIDE || d < 16) ? hot_lo : hot_hi;
+            const uint32_t nsg = (!WIDE || d < 16) ? nsg_lo : nsg_hi;
+            const uint32_t im = signmask(hot << (15 - (d & 15)));
+            const uint32_t nm = signmask(nsg << (15 - (d & 15))); // 0xFFFF where the old message was >= 0
+            const uint32_t mc = m0 ^ (x01 & im);
+            const uint32_t negold = vmax(vsub(mc ^ nm, nm), h2(-31)); // -(old message)
+            uint32_t x = vmin(vmax(vadd(l, negold), h2(-128)), h2(127)); // vqsub
+            if (d == 1 && first)
+                x &= 0xffff0000u; // node A (check 0) has no such link: neutral value
+            v[d] = x;
+            sx ^= x;
+            // |x| saturated to 127, minus beta = 1, floored at 0:  max(x - 1, ~x, 0), capped at 126
+            const uint32_t mg = vmin(vmax(vmax(vadd(x, h2(-1)), ~x), 0u), h2(126));
+            mag[d] = mg;
+            uint32_t key = mg * 32u + h2(d);
+            if (d == 1 && first)
+                key |= 0x00007fffu; // never the minimum
+            k1 = vmin(k1, vmax(k0, key));
+            k0 = vmin(k0, key);
+        } else {
+            v[d] = 0;
+            mag[d] = 0;
+        }
+    }
+    const uint32_t min0 = (k0 >> 5) & 0x07ff07ffu;
+    const uint32_t min1 = (k1 >> 5) & 0x07ff07ffu;
+    const uint32_t s01 = vadd(min0, min1);
+    uint32_t newsg_lo = 0, newsg_hi = 0, syn = 0, zer = 0;
+#pragma unroll
+    for (int d = 0; d < DEG_MAX; ++d) {
+        const bool live = (d < 2) || (d - 2 < lv.cnt);
+        if (live) {
+            // magnitude = min over the OTHER links = min0 + min1 - min(mag, min1)
+            const uint32_t m = vsub(s01, vmin(mag[d], min1));
+            const uint32_t ng = signmask(sx ^ v[d]); // product of the other signs, zero counts as +
+            const uint32_t out = vsub(m ^ ng, ng);
+            const uint32_t nl = vmin(vmax(vadd(v[d], out), h2(-128)), h2(127)); // vqadd
+            const uint32_t packed = prmt(nl, 0, sel[d] >> 16);
+            if (d == 1 && first)
+                L[adr[d]] = (int8_t)(nl >> 16); // only node B's link exists (low byte of that word)
+            else
+                *reinterpret_cast<uint16_t*>(L + adr[d]) = (uint16_t)packed;
+            const uint32_t bit = ng & 0x00010001u;
+            if (!WIDE || d < 16)
+                newsg_lo |= bit << (d & 15);
+            else
+                newsg_hi |= bit << (d & 15);
+            if (SELF_CHECK) {
+                uint32_t nlc = nl;
+                if (d == 1 && first)
+                    nlc = (nl & 0xffff0000u) | 1u; // absent link: positive, non-zero
+                syn ^= nlc;
+                zer |= vsub(nlc, h2(1)) & ~nlc; // bit 15 of a half set iff that half is 0
+            }
+        }
+    }
+    // ---- encode the new state ----
+    const uint32_t c0 = vmin(min0, h2(32)), c1 = vmin(min1, h2(32));
+    uint32_t nA = (c0 & 0xffffu) | ((c1 & 0xffffu) << 6) | ((k0 & 31u) << 12);
+    uint32_t nB = (c0 >> 16) | ((c1 >> 16) << 6) | (((k0 >> 16) & 31u) << 12);
+    if (!WIDE) {
+        nA |= (newsg_lo & 0x7fffu) << 17;
+        nB |= ((newsg_lo >> 16) & 0x7fffu) << 17;
+        __stcg(reinterpret_cast<uint2*>(msg_out), make_uint2(nA, nB));
+    } else {
+        const uint32_t tA = (newsg_lo & 0xffffu) | (newsg_hi << 16);
+        const uint32_t tB = (newsg_lo >> 16) | (newsg_hi & 0xffff0000u);
+        __stcg(reinterpret_cast<uint4*>(msg_out), make_uint4(nA, nB, tA, tB));
+    }
+    if (SELF_CHECK)
+        return (int)(((syn | zer) & 0x80008000u) != 0);
+    return 0;
+}
+
+// ---- one check node j of a conflict layer (scalar, same arithmetic) -------------------------------
+template <int CNT_MAX, bool WIDE, bool SELF_CHECK>
+__device__ __forceinline__ int process_cn(int8_t* __restrict__ L, const uint2* __restrict__ edges, const LayerView& lv, int layer,
+                                          int j, int K, int q, uint32_t* __restrict__ msg_pair, bool zero_state)
+{
+    constexpr int DEG_MAX = CNT_MAX + 2;
+    const int hsel = j >= kPairs; // which node of the pair
+    const int half = kPairs * q;
+    uint32_t w = 0, sg = 0;
+    if (!zero_state) {
+        w = __ldcg(msg_pair + hsel);
+        sg = WIDE ? __ldcg(msg_pair + 2 + hsel) : (w >> 17);
+    }
+    const int old_min0 = (int)(w & 63u), old_min1 = (int)((w >> 6) & 63u), old_arg = (int)((w >> 12) & 31u);
+    const int c = q * j + layer;
+    const bool has_prev = c > 0;
+    int adr[DEG_MAX], v[DEG_MAX];
+    adr[0] = parity_addr(K, half, c);
+    adr[1] = parity_addr(K, half, has_prev ? c - 1 : 0);
+#pragma unroll
+    for (int d = 0; d < CNT_MAX; ++d) {
+        if (d < lv.cnt) {
+            const uint32_t e0 = edges[lv.edge_begin + d].x;
+            const int ap = (int)((e0 >> 17) & 0xffu), ra = (int)((e0 >> 25) & 1u);
+            const int gbase = (int)(e0 & 0x1ffffu) - 360 + 2 * ap;
+            int s = j - ap - kPairs * ra; // (j - shift) mod 360, j < 360, shift < 360
+            s += (s < 0) ? 360 : 0;
+            adr[d + 2] = data_addr(gbase, s);
+        } else {
+            adr[d + 2] = 0;
+        }
+    }
+    int min0 = 127, min1 = 127, arg = 0, sx = 0;
 #pragma unroll
     for (int d = 0; d < DEG_MAX; ++d) {
         const bool live = (d == 0) || (d == 1 ? has_prev : (d - 2 < lv.cnt));
         if (live) {
             const int l = (int)L[adr[d]];
-            // stored message = clamp(+-m, -32, 31) rebuilt from the compressed state
             const int mc = (d == old_arg) ? old_min1 : old_min0;
-            const int old = ((old_signs >> d) & 1u) ? -mc : min(mc, 31);
-            const int x = clamp8(l - old);          // vqsub
+            const int old = ((sg >> d) & 1u) ? -mc : min(mc, 31);
+            const int x = min(max(l - old, -128), 127);
             v[d] = x;
             sx ^= x;
-            const int mag = max(min(abs(x), 127) - 1, 0); // vqabs, then unsigned vqsub beta=1
-            if (mag < min0) {
+            const int mg = max(min(abs(x), 127) - 1, 0);
+            if (mg < min0) {
                 min1 = min0;
-                min0 = mag;
+                min0 = mg;
                 arg = d;
             } else {
-                min1 = min(min1, mag);
+                min1 = min(min1, mg);
             }
         } else {
             v[d] = 0;
         }
     }
     uint32_t new_signs = 0;
+    int syn = 0, zer = 0;
 #pragma unroll
     for (int d = 0; d < DEG_MAX; ++d) {
         const bool live = (d == 0) || (d == 1 ? has_prev : (d - 2 < lv.cnt));
         if (live) {
             const int m = (d == arg) ? min1 : min0;
-            const bool neg = ((sx ^ v[d]) < 0); // product of the OTHER signs, zero counts as +
-            const int out = neg ? -m : m;
-            L[adr[d]] = (int8_t)clamp8(v[d] + out); // vqadd with the unclamped message
+            const bool neg = ((sx ^ v[d]) < 0);
+            const int nl = min(max(v[d] + (neg ? -m : m), -128), 127);
+            L[adr[d]] = (int8_t)nl;
             new_signs |= (neg ? 1u : 0u) << d;
+            if (SELF_CHECK) {
+                syn ^= nl;
+                zer |= (nl == 0);
+            }
         }
     }
     const uint32_t lo = (uint32_t)min(min0, 32) | ((uint32_t)min(min1, 32) << 6) | ((uint32_t)arg << 12);
-    if (MSG_WORDS == 1)
-        msg[cn] = lo | (new_signs << 17);
-    else
-        reinterpret_cast<uint2*>(msg)[cn] = make_uint2(lo, new_signs);
+    if (!WIDE) {
+        __stcg(msg_pair + hsel, lo | (new_signs << 17));
+    } else {
+        __stcg(msg_pair + hsel, lo);
+        __stcg(msg_pair + 2 + hsel, new_signs);
+    }
+    if (SELF_CHECK)
+        return (syn < 0) | zer;
+    return 0;
 }
 
-// lib/ldpc_decoder/layered_decoder.hh:32-49 for one check node: unsatisfied if the sign product
+// lib/ldpc_decoder/layered_decoder.hh:32-49 for the pair (p, p+180): unsatisfied if the sign product
 // is not +, and a zero LLR counts as unsatisfied (vsign(.,0) = 0, test is "> 0").
 template <int CNT_MAX>
-__device__ __forceinline__ int check_cn(const int8_t* __restrict__ L, const uint32_t* __restrict__ edges, const LayerView& lv,
-                                        int layer, int j, int K, int q)
+__device__ __forceinline__ uint32_t check_pair(const int8_t* __restrict__ L, const uint2* __restrict__ edges, const LayerView& lv,
+                                               int layer, int p, int K, int q)
 {
-    const int c = q * j + layer;
-    int x = (int)L[K + c];
-    int s = x;
-    int z = (x == 0);
-    if (c > 0) {
-        x = (int)L[K + c - 1];
-        s ^= x;
-        z |= (x == 0);
-    }
+    const int c = q * p + layer;
+    const bool first = (layer == 0 && p == 0);
+    uint32_t raw = *reinterpret_cast<const uint16_t*>(L + K + 2 * c);
+    uint32_t s = raw;
+    uint32_t z = (raw - 0x0101u) & ~raw;
+    if (!first)
+        raw = *reinterpret_cast<const uint16_t*>(L + K + 2 * c - 2);
+    else
+        raw = ((uint32_t)(uint8_t)L[K + 2 * (kPairs * q - 1)] << 8) | 0x01u; // node B's link only
+    s ^= raw;
+    z |= (raw - 0x0101u) & ~raw;
 #pragma unroll
     for (int d = 0; d < CNT_MAX; ++d) {
         if (d < lv.cnt) {
-            x = (int)L[edge_index(edges[lv.edge_begin + d], j)];
-            s ^= x;
-            z |= (x == 0);
+            const uint2 e = edges[lv.edge_begin + d];
+            const int ap = (int)((e.x >> 17) & 0xffu);
+            const bool lt = p < ap;
+            raw = *reinterpret_cast<const uint16_t*>(L + (int)(e.x & 0x1ffffu) + 2 * p - (lt ? 0 : 360));
+            z |= (raw - 0x0101u) & ~raw;
+            // bring node p's byte to the low position: swap iff (ra ^ lt)
+            const uint32_t swap = ((e.x >> 25) & 1u) ^ (lt ? 1u : 0u);
+            s ^= swap ? prmt(raw, 0, 0x4401) : raw;
         }
     }
-    return (s < 0) | z;
+    return (s | z) & 0x8080u;
 }
 
-template <int CNT_MAX, int MSG_WORDS>
-__global__ void __launch_bounds__(kLdpcThreads, 1) ldpc_decode_kernel(const LdpcLaunch p)
+template <int CNT_MAX, bool WIDE>
+__global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kernel(const LdpcLaunch p)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint32_t* msg = reinterpret_cast<uint32_t*>(smem + p.smem_msg_off);
-    const uint4* layers = reinterpret_cast<const uint4*>(smem + p.smem_tab_off);
-    const uint32_t* edges = reinterpret_cast<const uint32_t*>(smem + p.smem_tab_off + (size_t)p.q * 16);
+    int8_t* const L = reinterpret_cast<int8_t*>(smem);
+    const uint2* layers = reinterpret_cast<const uint2*>(smem + p.smem_tab_off);
+    const uint2* edges = reinterpret_cast<const uint2*>(smem + p.smem_tab_off + (size_t)p.q * 8);
+    const uint2* steps = reinterpret_cast<const uint2*>(smem + p.smem_tab_off + (size_t)p.q * 8 + (size_t)p.n_circ * 8);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + p.smem_bar_off);
+    __shared__ int s_group_bad;
 
     const int tid = threadIdx.x;
-    const int N = p.N, K = p.K, q = p.q;
-    const StepRecDev* __restrict__ steps = p.steps;
-    const uint16_t* __restrict__ order = p.order;
+    const int N = p.N, K = p.K, q = p.q, R = p.R;
+    const int half = R / 2;
+    constexpr int MW = WIDE ? 2 : 1; // state words per check node
+    uint32_t* const msg = p.msg_scratch + (size_t)blockIdx.x * R * MW;
+    const uint16_t* __restrict__ work = p.work;
 
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    uint32_t phase = 0;
-    // stage the code's circulant table once per CTA (TMA)
+    // stage the code tables once per CTA (TMA)
     if (tid == 0) {
         mbar_expect_tx(bar, p.tab_bytes);
         tma_load_1d(smem + p.smem_tab_off, p.tab, p.tab_bytes, bar);
     }
-    mbar_wait(bar, phase);
-    phase ^= 1;
+    mbar_wait(bar, 0);
 
     for (int f = blockIdx.x; f < p.frames; f += gridDim.x) {
-        // ---- soft input: HBM -> shared memory ----------------------------------------------
-        const int8_t* src = p.llr + (size_t)f * N;
-        // bulk copies need 16-byte aligned addresses and sizes on both sides: place the frame in
-        // shared memory with the same misalignment as its global address (16 spare bytes are
-        // reserved) and peel the unaligned head / tail with plain loads.
-        const uint32_t mis = (uint32_t)((uintptr_t)src & 15u);
-        int8_t* const L = reinterpret_cast<int8_t*>(smem) + mis;
+        // ---- soft input: HBM -> shared memory, into the pair-interleaved order --------------------
         {
-            const uint32_t head = mis ? (16u - mis) : 0u;
-            const uint32_t body = ((uint32_t)N - head) & ~15u;
-            const uint32_t tail = (uint32_t)N - head - body;
-            if (tid == 0) {
-                mbar_expect_tx(bar, body);
-                tma_load_1d(L + head, src + head, body, bar);
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(p.llr + (size_t)f * N);
+            const int data_chunks = K / 8; // 8 output bytes per chunk = 4 halfwords
+            for (int u = tid; u < N / 8; u += kLdpcThreads) {
+                int ia, ib, out;
+                if (u < data_chunks) {
+                    const int g = u / 45, w4 = u - g * 45;
+                    ia = g * 90 + w4; // word index of bytes g*360 + 4*w4 ..
+                    ib = ia + 45;     // + 180 bytes
+                    out = g * 360 + 8 * w4;
+                } else {
+                    const int up = u - data_chunks;
+                    ia = K / 4 + up;
+                    ib = ia + half / 4;
+                    out = K + 8 * up;
+                }
+                const uint32_t a = __ldcs(src + ia), b = __ldcs(src + ib);
+                *reinterpret_cast<uint2*>(L + out) = make_uint2(prmt(a, b, 0x5140), prmt(a, b, 0x7362));
             }
-            if (tid < (int)head)
-                L[tid] = src[tid];
-            if (tid >= 32 && tid < 32 + (int)tail)
-                L[head + body + (tid - 32)] = src[head + body + (tid - 32)];
         }
-        for (int i = tid; i < p.R * MSG_WORDS; i += kLdpcThreads) // reset(): layered_decoder.hh:27-31
-            msg[i] = 0;
-        mbar_wait(bar, phase);
-        phase ^= 1;
         __syncthreads();
 
-        // ---- while (bad() && --trials >= 0) update();  layered_decoder.hh:153 ----------------
+        // ---- while (bad() && --trials >= 0) update();  layered_decoder.hh:153 ----------------------
         int trials = p.max_trials;
         int iter = 0;
+        int bad;
+        int proven_bad = 0;
         for (;;) {
-            int flag = 0;
-            if (tid < kM) {
-                for (int i = 0; i < q; ++i) {
-                    const LayerView lv = load_layer(layers, i);
-                    flag |= check_cn<CNT_MAX>(L, edges, lv, i, tid, K, q);
+            if (!proven_bad) {
+                uint32_t flag = 0;
+                if (tid < kPairs) {
+                    for (int i = 0; i < q; ++i) {
+                        const LayerView lv = load_layer(layers, i);
+                        flag |= check_pair<CNT_MAX>(L, edges, lv, i, tid, K, q);
+                    }
                 }
+                bad = __syncthreads_or((int)flag);
+            } else {
+                bad = 1;
             }
-            int bad = __syncthreads_or(flag);
             if (p.group > 1) {
-                // reference batch semantics: the whole SIMD batch keeps iterating while any of
-                // its frames is bad.  One word per (group, iteration): low half counts
-                // arrivals, high half counts bad frames.  All CTAs of a group are co-resident
-                // (cooperative launch, grid a multiple of the group size).
-                __shared__ int s_group_bad;
+                // reference batch semantics: the whole SIMD batch keeps iterating while any of its
+                // frames is bad.  One word per (group, iteration): low half counts arrivals, high
+                // half counts bad frames.  All CTAs are co-resident (cooperative launch).
                 if (tid == 0) {
                     unsigned int* w = p.gsync + (size_t)(f / p.group) * (p.max_trials + 2) + iter;
                     __threadfence();
@@ -315,75 +451,114 @@ __global__ void __launch_bounds__(kLdpcThreads, 1) ldpc_decode_kernel(const Ldpc
             }
             if (!bad || --trials < 0)
                 break;
+            const bool zero_state = (iter == 0); // reset(): layered_decoder.hh:27-31, no memset needed
             ++iter;
-            for (int i = 0; i < q; ++i) {
-                const LayerView lv = load_layer(layers, i);
-                if (lv.n_steps == 1) {
-                    if (tid < kM)
-                        process_cn<CNT_MAX, MSG_WORDS>(L, msg, edges, lv, i, tid, K, q);
-                    __syncthreads();
-                } else {
-                    for (int s = 0; s < lv.n_steps; ++s) {
-                        const StepRecDev st = steps[lv.step_begin + s];
-                        if (tid < (int)st.count) {
-                            const int j = (int)order[lv.order_begin + st.begin + tid];
-                            process_cn<CNT_MAX, MSG_WORDS>(L, msg, edges, lv, i, j, K, q);
-                        }
-                        __syncthreads();
+
+            // ---- one iteration: walk the step list ---------------------------------------------------
+            int self_bad = 0;
+            uint2 st = steps[0];
+            uint32_t wA = 0, wB = 0, sA = 0, sB = 0;
+            // state words of a pair step, fetched one step ahead of their use
+            auto prefetch = [&](uint2 s) {
+                if ((s.x >> 16) == 0 && tid < kPairs && !zero_state) {
+                    const uint32_t* m = msg + ((size_t)(s.x & 0xffffu) * kPairs + tid) * 2 * MW;
+                    if (!WIDE) {
+                        const uint2 t = __ldcg(reinterpret_cast<const uint2*>(m));
+                        wA = t.x, wB = t.y;
+                    } else {
+                        const uint4 t = __ldcg(reinterpret_cast<const uint4*>(m));
+                        wA = t.x, wB = t.y, sA = t.z, sB = t.w;
                     }
                 }
+            };
+            prefetch(st);
+            for (int s = 0; s < p.n_steps; ++s) {
+                const int layer = (int)(st.x & 0xffffu), count = (int)(st.x >> 16);
+                const uint32_t work_off = st.y;
+                const LayerView lv = load_layer(layers, layer);
+                const bool last = (s == p.n_steps - 1);
+                const uint32_t cA = wA, cB = wB, csA = sA, csB = sB;
+                if (!last) {
+                    st = steps[s + 1];
+                    prefetch(st); // the next layer's state words travel while this layer computes
+                }
+                if (count == 0) {
+                    if (tid < kPairs) {
+                        uint32_t* mo = msg + ((size_t)layer * kPairs + tid) * 2 * MW;
+                        if (last)
+                            self_bad |= process_pair<CNT_MAX, WIDE, true>(L, edges, lv, layer, tid, K, q, cA, cB, csA, csB, mo);
+                        else
+                            process_pair<CNT_MAX, WIDE, false>(L, edges, lv, layer, tid, K, q, cA, cB, csA, csB, mo);
+                    }
+                } else {
+                    for (int t = tid; t < count; t += kLdpcThreads) {
+                        const int j = (int)work[work_off + t];
+                        const int pp = j >= kPairs ? j - kPairs : j;
+                        uint32_t* mp = msg + ((size_t)layer * kPairs + pp) * 2 * MW;
+                        if (last)
+                            self_bad |= process_cn<CNT_MAX, WIDE, true>(L, edges, lv, layer, j, K, q, mp, zero_state);
+                        else
+                            process_cn<CNT_MAX, WIDE, false>(L, edges, lv, layer, j, K, q, mp, zero_state);
+                    }
+                }
+                if (last)
+                    proven_bad = __syncthreads_or(self_bad);
+                else
+                    __syncthreads();
             }
         }
 
-        // ---- outputs ---------------------------------------------------------------------------
-        // posteriors were written through the generic proxy; the TMA store below and the next
-        // frame's TMA load go through the async proxy
-        fence_proxy_async();
-        __syncthreads();
+        // ---- outputs -----------------------------------------------------------------------------------
         if (p.trials_left && tid == 0)
             p.trials_left[f] = trials;
         if (p.hard) {
             // llr < 0 -> 1, MSB first: lib/ldpc_decoder_bb_impl.cc:432-442
             uint8_t* dst = p.hard + (size_t)f * p.out_bytes;
-            if ((mis & 7u) == 0) {
-                const uint2* L8 = reinterpret_cast<const uint2*>(L);
-                for (int b = tid; b < p.out_bytes; b += kLdpcThreads) {
-                    const uint2 w = L8[b];
-                    const uint32_t hi4 = ((((w.x >> 7) & 0x01010101u) * 0x08040201u) >> 24) & 0xFu;
-                    const uint32_t lo4 = ((((w.y >> 7) & 0x01010101u) * 0x08040201u) >> 24) & 0xFu;
-                    dst[b] = (uint8_t)((hi4 << 4) | lo4);
-                }
-            } else {
-                for (int b = tid; b < p.out_bytes; b += kLdpcThreads) {
-                    uint32_t v = 0;
+            for (int b = tid; b < p.out_bytes; b += kLdpcThreads) {
+                const int n0 = 8 * b;
+                uint32_t acc = 0;
+                if (n0 < K) { // 8 consecutive bits of one 360-bit group (8 | 360)
+                    const int g = n0 / 360, m = n0 - g * 360;
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
-                        v |= (L[8 * b + k] < 0 ? 1u : 0u) << (7 - k);
-                    dst[b] = (uint8_t)v;
+                        acc |= (L[data_addr(g * 360, m + k)] < 0 ? 1u : 0u) << (7 - k);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        acc |= (L[parity_addr(K, half, n0 - K + k)] < 0 ? 1u : 0u) << (7 - k);
                 }
+                dst[b] = (uint8_t)acc;
             }
         }
         if (p.llr_post) {
-            int8_t* dst = p.llr_post + (size_t)f * N;
-            if ((((uintptr_t)dst) & 15u) == 0 && (N & 15) == 0 && mis == 0) {
-                if (tid == 0) {
-                    tma_store_1d(dst, L, (uint32_t)N);
-                    tma_store_commit();
-                    tma_store_wait_read();
+            uint32_t* dst = reinterpret_cast<uint32_t*>(p.llr_post + (size_t)f * N);
+            const int data_chunks = K / 8;
+            for (int u = tid; u < N / 8; u += kLdpcThreads) {
+                int ia, ib, in;
+                if (u < data_chunks) {
+                    const int g = u / 45, w4 = u - g * 45;
+                    ia = g * 90 + w4;
+                    ib = ia + 45;
+                    in = g * 360 + 8 * w4;
+                } else {
+                    const int up = u - data_chunks;
+                    ia = K / 4 + up;
+                    ib = ia + half / 4;
+                    in = K + 8 * up;
                 }
-            } else {
-                for (int i = tid; i < N; i += kLdpcThreads)
-                    dst[i] = L[i];
+                const uint2 w = *reinterpret_cast<const uint2*>(L + in);
+                dst[ia] = prmt(w.x, w.y, 0x6420);
+                dst[ib] = prmt(w.x, w.y, 0x7531);
             }
         }
         __syncthreads(); // L is reused by the next frame
     }
 }
 
-template <int CNT_MAX, int MSG_WORDS>
+template <int CNT_MAX, bool WIDE>
 cudaError_t launch_one(const LdpcLaunch& p, int grid, size_t smem, cudaStream_t stream)
 {
-    auto kern = ldpc_decode_kernel<CNT_MAX, MSG_WORDS>;
+    auto kern = ldpc_decode_kernel<CNT_MAX, WIDE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess)
         return e;
@@ -395,15 +570,23 @@ cudaError_t launch_one(const LdpcLaunch& p, int grid, size_t smem, cudaStream_t 
     return cudaGetLastError();
 }
 
+template <int CNT_MAX, bool WIDE>
+int occupancy_one(size_t smem)
+{
+    auto kern = ldpc_decode_kernel<CNT_MAX, WIDE>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return 0;
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kLdpcThreads, smem) != cudaSuccess)
+        return 0;
+    return n;
+}
+
 } // namespace
 
-size_t ldpc_smem_bytes(int N, int R, int msg_words, uint32_t tab_bytes, LdpcLaunch* p)
+size_t ldpc_smem_bytes(int N, uint32_t tab_bytes, LdpcLaunch* p)
 {
-    size_t off = (((size_t)N + 15) & ~(size_t)15) + 16; // +16: frames keep their global misalignment
-    if (p)
-        p->smem_msg_off = (uint32_t)off;
-    off += (size_t)R * msg_words * 4;
-    off = (off + 15) & ~(size_t)15;
+    size_t off = ((size_t)N + 15) & ~(size_t)15;
     if (p)
         p->smem_tab_off = (uint32_t)off;
     off += tab_bytes;
@@ -414,21 +597,30 @@ size_t ldpc_smem_bytes(int N, int R, int msg_words, uint32_t tab_bytes, LdpcLaun
     return off;
 }
 
-cudaError_t ldpc_launch(const LdpcLaunch& p, int max_cnt, int msg_words, int grid, size_t smem, cudaStream_t stream)
+#define DVBS2_DISPATCH(CALL)                             \
+    if (max_cnt <= 4 && !wide) return CALL(4, false);    \
+    if (max_cnt <= 6 && !wide) return CALL(6, false);    \
+    if (max_cnt <= 8 && !wide) return CALL(8, false);    \
+    if (max_cnt <= 10 && !wide) return CALL(10, false);  \
+    if (max_cnt <= 13 && !wide) return CALL(13, false);  \
+    if (max_cnt <= 16 && wide) return CALL(16, true);    \
+    if (max_cnt <= 20 && wide) return CALL(20, true);    \
+    if (max_cnt <= 28 && wide) return CALL(28, true);
+
+cudaError_t ldpc_launch(const LdpcLaunch& p, int max_cnt, bool wide, int grid, size_t smem, cudaStream_t stream)
 {
-#define DVBS2_CASE(C, W)                   \
-    if (max_cnt <= C && msg_words == W)    \
-        return launch_one<C, W>(p, grid, smem, stream);
-    DVBS2_CASE(4, 1)
-    DVBS2_CASE(6, 1)
-    DVBS2_CASE(8, 1)
-    DVBS2_CASE(10, 1)
-    DVBS2_CASE(13, 1)
-    DVBS2_CASE(16, 2)
-    DVBS2_CASE(20, 2)
-    DVBS2_CASE(28, 2)
-#undef DVBS2_CASE
+#define CALL(C, W) launch_one<C, W>(p, grid, smem, stream)
+    DVBS2_DISPATCH(CALL)
+#undef CALL
     return cudaErrorInvalidValue;
+}
+
+int ldpc_ctas_per_sm(int max_cnt, bool wide, size_t smem)
+{
+#define CALL(C, W) occupancy_one<C, W>(smem)
+    DVBS2_DISPATCH(CALL)
+#undef CALL
+    return 0;
 }
 
 } // namespace dvbs2b200
