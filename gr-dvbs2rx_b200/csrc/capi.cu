@@ -133,7 +133,7 @@ int create_from_blob(dvbs2b200_code** out, int device, std::vector<uint8_t>&& bl
         return bail(cuda_fail(e, "cudaMemcpy(tables)"));
     h->ldpc_smem = ldpc_smem_bytes(h->hdr.N, h->hdr.smem_bytes, nullptr);
     if (h->hdr.max_cnt <= 28 && h->ldpc_smem <= (size_t)h->smem_optin)
-        h->ldpc_ctas = ldpc_ctas_per_sm(h->hdr.max_cnt, h->hdr.msg_words == 2, h->ldpc_smem);
+        h->ldpc_ctas = ldpc_ctas_per_sm(h->hdr.max_cnt, h->hdr.uniform_cnt != 0, h->ldpc_smem);
     *out = h;
     return DVBS2B200_OK;
 }
@@ -227,7 +227,7 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
         CU(cudaMemsetAsync(h->d_sync.p, 0, words * sizeof(unsigned), stream));
         p.gsync = (unsigned*)h->d_sync.p;
     }
-    cudaError_t e = ldpc_launch(p, hd.max_cnt, hd.msg_words == 2, grid, smem, stream);
+    cudaError_t e = ldpc_launch(p, hd.max_cnt, hd.uniform_cnt != 0, grid, smem, stream);
     if (e != cudaSuccess)
         return cuda_fail(e, "ldpc_launch");
     h->launches += 1;

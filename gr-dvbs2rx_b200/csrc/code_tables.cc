@@ -54,6 +54,7 @@ void build_schedule(const LdpcTableDef& def, Schedule& s)
         L.edge_begin = (uint32_t)s.edges.size();
         L.cnt = (uint16_t)circ.size();
         s.max_cnt = std::max(s.max_cnt, (int)circ.size());
+        s.min_cnt = std::min(s.min_cnt, (int)circ.size());
         bool conflict = false;
         for (size_t a = 0; a < circ.size(); ++a) {
             s.edges.push_back(pack_edge(circ[a].first, circ[a].second));
@@ -220,11 +221,12 @@ bool build_blob(int standard, int framesize, int rate, std::vector<uint8_t>& blo
     h.gf_m = poly_m(pp);
     h.kldpc_out = mc->nbch;
     // compressed check-node state: 6+6 bits of clamped minima, 5 bits argmin, 1 sign bit/link
-    h.msg_words = (17 + h.max_cn_deg <= 32) ? 1 : 2;
+    h.msg_words = (s.max_cnt <= 13) ? 1 : 2; // must agree with ldpc_wide_state()
     h.n_steps_total = (int32_t)s.steps.size();
     h.n_conflict_layers = s.conflict_layers;
     h.steps_per_iter = s.steps_per_iter;
     h.max_depth = s.max_depth;
+    h.uniform_cnt = (s.min_cnt == s.max_cnt) ? 1 : 0;
     h.bch_shorten = ((1u << h.gf_m) - 1) - (uint32_t)mc->nbch;
 
     size_t off = sizeof(BlobHeader);

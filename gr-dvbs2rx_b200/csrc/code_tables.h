@@ -29,7 +29,7 @@ const ModcodDef* find_modcod(int standard, int framesize, int rate);
 
 // ---- packed blob ---------------------------------------------------------------------------
 constexpr uint32_t kBlobMagic = 0x32425344u; // "DSB2"
-constexpr uint32_t kBlobVersion = 4;
+constexpr uint32_t kBlobVersion = 5;
 
 // One per layer, 8 bytes, lives in shared memory.
 struct LayerRec {
@@ -39,7 +39,7 @@ struct LayerRec {
 };
 // One per circulant, 8 bytes, lives in shared memory (see pack_edge).
 struct EdgeRec {
-    uint32_t e0; // hi | a' << 17 | ra << 25
+    uint32_t e0; // hi | a' << 16   (hi <= 65160 fits 16 bits)
     uint32_t e1; // PRMT selectors for p >= a': unpack | pack << 16
 };
 // One per schedule step of an iteration, 8 bytes, lives in shared memory.  A conflict-free layer
@@ -61,13 +61,15 @@ struct BlobHeader {
     int32_t msg_words;  // 32-bit words of compressed message state per check node (1 or 2)
     int32_t n_steps_total, n_conflict_layers;
     int32_t steps_per_iter, max_depth;
+    int32_t uniform_cnt; // 1 if every layer has max_cnt data links per check node
+    int32_t reserved2;
     // section offsets from the start of the blob, all 16-byte aligned
     uint32_t smem_off, smem_bytes; // [LayerRec q][EdgeRec n_circ][StepRec steps_per_iter]: TMA-staged
     uint32_t layer_off, edge_off;  // (inside the smem section)
     uint32_t step_off, order_off;  // StepRec[] (inside the smem section), uint16 work[] (global)
     uint32_t antilog_off, log_off; // uint16[2^m] each: alpha^i (i < 2^m-1), log(x)
     uint32_t bch_shorten;          // s = 2^m - 1 - nbch
-    uint32_t reserved1[5];
+    uint32_t reserved1[3];
 };
 static_assert(sizeof(BlobHeader) % 16 == 0, "header must keep sections 16-byte aligned");
 
@@ -76,12 +78,12 @@ static_assert(sizeof(BlobHeader) % 16 == 0, "header must keep sections 16-byte a
 // two check nodes p and p+180 of a layer always find their operands in ONE 16-bit word.
 // Check-node pair p reads, through circulant (group, shift = a' + 180*ra), the halfword at
 //   hi + 2p - (p >= a' ? 360 : 0),   hi = group*360 + 360 - 2a';
-// node p is the low byte iff (ra ^ (p < a')) == 0.
+// node p is the low byte iff (ra ^ (p < a')) == 0; ra is bit 0 of the unpack selector.
 inline EdgeRec pack_edge(int group, int shift)
 {
     const int ap = shift % 180, ra = shift / 180;
     EdgeRec e;
-    e.e0 = (uint32_t)(group * 360 + 360 - 2 * ap) | ((uint32_t)ap << 17) | ((uint32_t)ra << 25);
+    e.e0 = (uint32_t)(group * 360 + 360 - 2 * ap) | ((uint32_t)ap << 16);
     // PRMT selectors when p >= a' (r = ra); the kernel XORs 0x1111 / 0x0022 when p < a'
     const uint32_t unpack = ra ? 0x8091u : 0x9180u; // bytes -> sign-extended s16x2 [node p | node p+180]
     const uint32_t pack = ra ? 0x4402u : 0x4420u;   // s16x2 -> two bytes in memory order
@@ -99,7 +101,7 @@ struct Schedule {
     std::vector<EdgeRec> edges;
     std::vector<StepRec> steps; // one iteration, in execution order
     std::vector<uint16_t> order; // work[]: check-node indices of the conflict steps
-    int max_cnt = 0, steps_per_iter = 0, max_depth = 0, conflict_layers = 0;
+    int max_cnt = 0, min_cnt = 1 << 30, steps_per_iter = 0, max_depth = 0, conflict_layers = 0;
 };
 void build_schedule(const LdpcTableDef& def, Schedule& s);
 

@@ -88,6 +88,55 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 // 0xFFFF in every half whose bit 15 is set
 __device__ __forceinline__ uint32_t signmask(uint32_t x) { return prmt(x, 0, 0xBB99); }
 
+// L2 eviction policies: the check-node state is re-read every iteration and must stay L2
+// resident (evict_last); the soft input streams through once (evict_first).
+__device__ __forceinline__ uint64_t policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint32_t ldg_hint(const uint32_t* p, uint64_t pol)
+{
+    uint32_t r;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg_hint(const uint2* p, uint64_t pol)
+{
+    uint2 r;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_hint(const uint4* p, uint64_t pol)
+{
+    uint4 r;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void stg_hint(uint32_t* p, uint32_t v, uint64_t pol)
+{
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stg_hint(uint2* p, uint2 v, uint64_t pol)
+{
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stg_hint(uint4* p, uint4 v, uint64_t pol)
+{
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w), "l"(pol)
+                 : "memory");
+}
+
 struct LayerView {
     uint32_t edge_begin;
     int cnt;
@@ -112,10 +161,10 @@ __device__ __forceinline__ int parity_addr(int K, int half, int c) { return K + 
 
 // ---- two check nodes (p, p + 180) of a conflict-free layer ---------------------------------------
 // lib/ldpc_decoder/layered_decoder.hh:57-76 + algorithms.hh:170-206, both nodes at once.
-template <int CNT_MAX, bool WIDE, bool SELF_CHECK>
+template <int CNT_MAX, bool UNIFORM, bool WIDE, bool SELF_CHECK>
 __device__ __forceinline__ int process_pair(int8_t* __restrict__ L, const uint2* __restrict__ edges, const LayerView& lv, int layer,
                                             int p, int K, int q, uint32_t wA, uint32_t wB, uint32_t sA, uint32_t sB,
-                                            uint32_t* __restrict__ msg_out)
+                                            uint32_t* __restrict__ msg_out, uint64_t pol)
 {
     constexpr int DEG_MAX = CNT_MAX + 2;
     const bool first = (layer == 0 && p == 0); // check 0 has no previous parity link; check 180*q does
@@ -146,13 +195,13 @@ __device__ __forceinline__ int process_pair(int8_t* __restrict__ L, const uint2*
     // the word of parity bit 180q - 1 holds node B's previous parity bit in its LOW byte
     adr[1] = first ? K + 2 * (half - 1) : K + 2 * c - 2;
     sel[1] = first ? (0x8091u | (0x4402u << 16)) : sel[0];
+    const uint32_t pkey = ((uint32_t)p << 16) | 0xffffu; // e.x > pkey  <=>  p < a'
 #pragma unroll
     for (int d = 0; d < CNT_MAX; ++d) {
-        if (d < lv.cnt) {
+        if (UNIFORM || d < lv.cnt) {
             const uint2 e = edges[lv.edge_begin + d];
-            const int ap = (int)((e.x >> 17) & 0xffu);
-            const bool lt = p < ap;
-            adr[d + 2] = (int)(e.x & 0x1ffffu) + 2 * p - (lt ? 0 : 360);
+            const bool lt = e.x > pkey;
+            adr[d + 2] = (int)(e.x & 0xffffu) + 2 * p - (lt ? 0 : 360);
             sel[d + 2] = lt ? (e.y ^ 0x00221111u) : e.y;
         } else {
             adr[d + 2] = 0;
@@ -163,7 +212,7 @@ __device__ __forceinline__ int process_pair(int8_t* __restrict__ L, const uint2*
     uint32_t k0 = h2(0x7fff), k1 = h2(0x7fff), sx = 0;
 #pragma unroll
     for (int d = 0; d < DEG_MAX; ++d) {
-        const bool live = (d < 2) || (d - 2 < lv.cnt);
+        const bool live = UNIFORM || (d < 2) || (d - 2 < lv.cnt);
         if (live) {
             const uint32_t raw = *reinterpret_cast<const uint16_t*>(L + adr[d]);
             const uint32_t l = prmt(raw, 0, sel[d] & 0xffffu);
@@ -198,7 +247,7 @@ __device__ __forceinline__ int process_pair(int8_t* __restrict__ L, const uint2*
     uint32_t newsg_lo = 0, newsg_hi = 0, syn = 0, zer = 0;
 #pragma unroll
     for (int d = 0; d < DEG_MAX; ++d) {
-        const bool live = (d < 2) || (d - 2 < lv.cnt);
+        const bool live = UNIFORM || (d < 2) || (d - 2 < lv.cnt);
         if (live) {
             // magnitude = min over the OTHER links = min0 + min1 - min(mag, min1)
             const uint32_t m = vsub(s01, vmin(mag[d], min1));
@@ -231,11 +280,11 @@ __device__ __forceinline__ int process_pair(int8_t* __restrict__ L, const uint2*
     if (!WIDE) {
         nA |= (newsg_lo & 0x7fffu) << 17;
         nB |= ((newsg_lo >> 16) & 0x7fffu) << 17;
-        __stcg(reinterpret_cast<uint2*>(msg_out), make_uint2(nA, nB));
+        stg_hint(reinterpret_cast<uint2*>(msg_out), make_uint2(nA, nB), pol);
     } else {
         const uint32_t tA = (newsg_lo & 0xffffu) | (newsg_hi << 16);
         const uint32_t tB = (newsg_lo >> 16) | (newsg_hi & 0xffff0000u);
-        __stcg(reinterpret_cast<uint4*>(msg_out), make_uint4(nA, nB, tA, tB));
+        stg_hint(reinterpret_cast<uint4*>(msg_out), make_uint4(nA, nB, tA, tB), pol);
     }
     if (SELF_CHECK)
         return (int)(((syn | zer) & 0x80008000u) != 0);
@@ -243,17 +292,17 @@ __device__ __forceinline__ int process_pair(int8_t* __restrict__ L, const uint2*
 }
 
 // ---- one check node j of a conflict layer (scalar, same arithmetic) -------------------------------
-template <int CNT_MAX, bool WIDE, bool SELF_CHECK>
+template <int CNT_MAX, bool UNIFORM, bool WIDE, bool SELF_CHECK>
 __device__ __forceinline__ int process_cn(int8_t* __restrict__ L, const uint2* __restrict__ edges, const LayerView& lv, int layer,
-                                          int j, int K, int q, uint32_t* __restrict__ msg_pair, bool zero_state)
+                                          int j, int K, int q, uint32_t* __restrict__ msg_pair, bool zero_state, uint64_t pol)
 {
     constexpr int DEG_MAX = CNT_MAX + 2;
     const int hsel = j >= kPairs; // which node of the pair
     const int half = kPairs * q;
     uint32_t w = 0, sg = 0;
     if (!zero_state) {
-        w = __ldcg(msg_pair + hsel);
-        sg = WIDE ? __ldcg(msg_pair + 2 + hsel) : (w >> 17);
+        w = ldg_hint(msg_pair + hsel, pol);
+        sg = WIDE ? ldg_hint(msg_pair + 2 + hsel, pol) : (w >> 17);
     }
     const int old_min0 = (int)(w & 63u), old_min1 = (int)((w >> 6) & 63u), old_arg = (int)((w >> 12) & 31u);
     const int c = q * j + layer;
@@ -263,10 +312,10 @@ __device__ __forceinline__ int process_cn(int8_t* __restrict__ L, const uint2* _
     adr[1] = parity_addr(K, half, has_prev ? c - 1 : 0);
 #pragma unroll
     for (int d = 0; d < CNT_MAX; ++d) {
-        if (d < lv.cnt) {
-            const uint32_t e0 = edges[lv.edge_begin + d].x;
-            const int ap = (int)((e0 >> 17) & 0xffu), ra = (int)((e0 >> 25) & 1u);
-            const int gbase = (int)(e0 & 0x1ffffu) - 360 + 2 * ap;
+        if (UNIFORM || d < lv.cnt) {
+            const uint2 e = edges[lv.edge_begin + d];
+            const int ap = (int)(e.x >> 16), ra = (int)(e.y & 1u);
+            const int gbase = (int)(e.x & 0xffffu) - 360 + 2 * ap;
             int s = j - ap - kPairs * ra; // (j - shift) mod 360, j < 360, shift < 360
             s += (s < 0) ? 360 : 0;
             adr[d + 2] = data_addr(gbase, s);
@@ -277,7 +326,7 @@ __device__ __forceinline__ int process_cn(int8_t* __restrict__ L, const uint2* _
     int min0 = 127, min1 = 127, arg = 0, sx = 0;
 #pragma unroll
     for (int d = 0; d < DEG_MAX; ++d) {
-        const bool live = (d == 0) || (d == 1 ? has_prev : (d - 2 < lv.cnt));
+        const bool live = (d == 0) || (d == 1 ? has_prev : (UNIFORM || d - 2 < lv.cnt));
         if (live) {
             const int l = (int)L[adr[d]];
             const int mc = (d == old_arg) ? old_min1 : old_min0;
@@ -301,7 +350,7 @@ __device__ __forceinline__ int process_cn(int8_t* __restrict__ L, const uint2* _
     int syn = 0, zer = 0;
 #pragma unroll
     for (int d = 0; d < DEG_MAX; ++d) {
-        const bool live = (d == 0) || (d == 1 ? has_prev : (d - 2 < lv.cnt));
+        const bool live = (d == 0) || (d == 1 ? has_prev : (UNIFORM || d - 2 < lv.cnt));
         if (live) {
             const int m = (d == arg) ? min1 : min0;
             const bool neg = ((sx ^ v[d]) < 0);
@@ -316,10 +365,10 @@ __device__ __forceinline__ int process_cn(int8_t* __restrict__ L, const uint2* _
     }
     const uint32_t lo = (uint32_t)min(min0, 32) | ((uint32_t)min(min1, 32) << 6) | ((uint32_t)arg << 12);
     if (!WIDE) {
-        __stcg(msg_pair + hsel, lo | (new_signs << 17));
+        stg_hint(msg_pair + hsel, lo | (new_signs << 17), pol);
     } else {
-        __stcg(msg_pair + hsel, lo);
-        __stcg(msg_pair + 2 + hsel, new_signs);
+        stg_hint(msg_pair + hsel, lo, pol);
+        stg_hint(msg_pair + 2 + hsel, new_signs, pol);
     }
     if (SELF_CHECK)
         return (syn < 0) | zer;
@@ -328,7 +377,7 @@ __device__ __forceinline__ int process_cn(int8_t* __restrict__ L, const uint2* _
 
 // lib/ldpc_decoder/layered_decoder.hh:32-49 for the pair (p, p+180): unsatisfied if the sign product
 // is not +, and a zero LLR counts as unsatisfied (vsign(.,0) = 0, test is "> 0").
-template <int CNT_MAX>
+template <int CNT_MAX, bool UNIFORM>
 __device__ __forceinline__ uint32_t check_pair(const int8_t* __restrict__ L, const uint2* __restrict__ edges, const LayerView& lv,
                                                int layer, int p, int K, int q)
 {
@@ -343,23 +392,23 @@ __device__ __forceinline__ uint32_t check_pair(const int8_t* __restrict__ L, con
         raw = ((uint32_t)(uint8_t)L[K + 2 * (kPairs * q - 1)] << 8) | 0x01u; // node B's link only
     s ^= raw;
     z |= (raw - 0x0101u) & ~raw;
+    const uint32_t pkey = ((uint32_t)p << 16) | 0xffffu;
 #pragma unroll
     for (int d = 0; d < CNT_MAX; ++d) {
-        if (d < lv.cnt) {
+        if (UNIFORM || d < lv.cnt) {
             const uint2 e = edges[lv.edge_begin + d];
-            const int ap = (int)((e.x >> 17) & 0xffu);
-            const bool lt = p < ap;
-            raw = *reinterpret_cast<const uint16_t*>(L + (int)(e.x & 0x1ffffu) + 2 * p - (lt ? 0 : 360));
+            const bool lt = e.x > pkey;
+            raw = *reinterpret_cast<const uint16_t*>(L + (int)(e.x & 0xffffu) + 2 * p - (lt ? 0 : 360));
             z |= (raw - 0x0101u) & ~raw;
             // bring node p's byte to the low position: swap iff (ra ^ lt)
-            const uint32_t swap = ((e.x >> 25) & 1u) ^ (lt ? 1u : 0u);
+            const uint32_t swap = (e.y & 1u) ^ (lt ? 1u : 0u);
             s ^= swap ? prmt(raw, 0, 0x4401) : raw;
         }
     }
     return (s | z) & 0x8080u;
 }
 
-template <int CNT_MAX, bool WIDE>
+template <int CNT_MAX, bool UNIFORM, bool WIDE>
 __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kernel(const LdpcLaunch p)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -376,6 +425,7 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
     constexpr int MW = WIDE ? 2 : 1; // state words per check node
     uint32_t* const msg = p.msg_scratch + (size_t)blockIdx.x * R * MW;
     const uint16_t* __restrict__ work = p.work;
+    const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
 
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -407,7 +457,7 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
                     ib = ia + half / 4;
                     out = K + 8 * up;
                 }
-                const uint32_t a = __ldcs(src + ia), b = __ldcs(src + ib);
+                const uint32_t a = ldg_hint(src + ia, pol_stream), b = ldg_hint(src + ib, pol_stream);
                 *reinterpret_cast<uint2*>(L + out) = make_uint2(prmt(a, b, 0x5140), prmt(a, b, 0x7362));
             }
         }
@@ -424,7 +474,7 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
                 if (tid < kPairs) {
                     for (int i = 0; i < q; ++i) {
                         const LayerView lv = load_layer(layers, i);
-                        flag |= check_pair<CNT_MAX>(L, edges, lv, i, tid, K, q);
+                        flag |= check_pair<CNT_MAX, UNIFORM>(L, edges, lv, i, tid, K, q);
                     }
                 }
                 bad = __syncthreads_or((int)flag);
@@ -463,10 +513,10 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
                 if ((s.x >> 16) == 0 && tid < kPairs && !zero_state) {
                     const uint32_t* m = msg + ((size_t)(s.x & 0xffffu) * kPairs + tid) * 2 * MW;
                     if (!WIDE) {
-                        const uint2 t = __ldcg(reinterpret_cast<const uint2*>(m));
+                        const uint2 t = ldg_hint(reinterpret_cast<const uint2*>(m), pol_keep);
                         wA = t.x, wB = t.y;
                     } else {
-                        const uint4 t = __ldcg(reinterpret_cast<const uint4*>(m));
+                        const uint4 t = ldg_hint(reinterpret_cast<const uint4*>(m), pol_keep);
                         wA = t.x, wB = t.y, sA = t.z, sB = t.w;
                     }
                 }
@@ -486,9 +536,9 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
                     if (tid < kPairs) {
                         uint32_t* mo = msg + ((size_t)layer * kPairs + tid) * 2 * MW;
                         if (last)
-                            self_bad |= process_pair<CNT_MAX, WIDE, true>(L, edges, lv, layer, tid, K, q, cA, cB, csA, csB, mo);
+                            self_bad |= process_pair<CNT_MAX, UNIFORM, WIDE, true>(L, edges, lv, layer, tid, K, q, cA, cB, csA, csB, mo, pol_keep);
                         else
-                            process_pair<CNT_MAX, WIDE, false>(L, edges, lv, layer, tid, K, q, cA, cB, csA, csB, mo);
+                            process_pair<CNT_MAX, UNIFORM, WIDE, false>(L, edges, lv, layer, tid, K, q, cA, cB, csA, csB, mo, pol_keep);
                     }
                 } else {
                     for (int t = tid; t < count; t += kLdpcThreads) {
@@ -496,9 +546,9 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
                         const int pp = j >= kPairs ? j - kPairs : j;
                         uint32_t* mp = msg + ((size_t)layer * kPairs + pp) * 2 * MW;
                         if (last)
-                            self_bad |= process_cn<CNT_MAX, WIDE, true>(L, edges, lv, layer, j, K, q, mp, zero_state);
+                            self_bad |= process_cn<CNT_MAX, UNIFORM, WIDE, true>(L, edges, lv, layer, j, K, q, mp, zero_state, pol_keep);
                         else
-                            process_cn<CNT_MAX, WIDE, false>(L, edges, lv, layer, j, K, q, mp, zero_state);
+                            process_cn<CNT_MAX, UNIFORM, WIDE, false>(L, edges, lv, layer, j, K, q, mp, zero_state, pol_keep);
                     }
                 }
                 if (last)
@@ -555,10 +605,10 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
     }
 }
 
-template <int CNT_MAX, bool WIDE>
+template <int CNT_MAX, bool UNIFORM, bool WIDE>
 cudaError_t launch_one(const LdpcLaunch& p, int grid, size_t smem, cudaStream_t stream)
 {
-    auto kern = ldpc_decode_kernel<CNT_MAX, WIDE>;
+    auto kern = ldpc_decode_kernel<CNT_MAX, UNIFORM, WIDE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess)
         return e;
@@ -570,10 +620,10 @@ cudaError_t launch_one(const LdpcLaunch& p, int grid, size_t smem, cudaStream_t 
     return cudaGetLastError();
 }
 
-template <int CNT_MAX, bool WIDE>
+template <int CNT_MAX, bool UNIFORM, bool WIDE>
 int occupancy_one(size_t smem)
 {
-    auto kern = ldpc_decode_kernel<CNT_MAX, WIDE>;
+    auto kern = ldpc_decode_kernel<CNT_MAX, UNIFORM, WIDE>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return 0;
     int n = 0;
@@ -597,30 +647,51 @@ size_t ldpc_smem_bytes(int N, uint32_t tab_bytes, LdpcLaunch* p)
     return off;
 }
 
-#define DVBS2_DISPATCH(CALL)                             \
-    if (max_cnt <= 4 && !wide) return CALL(4, false);    \
-    if (max_cnt <= 6 && !wide) return CALL(6, false);    \
-    if (max_cnt <= 8 && !wide) return CALL(8, false);    \
-    if (max_cnt <= 10 && !wide) return CALL(10, false);  \
-    if (max_cnt <= 13 && !wide) return CALL(13, false);  \
-    if (max_cnt <= 16 && wide) return CALL(16, true);    \
-    if (max_cnt <= 20 && wide) return CALL(20, true);    \
-    if (max_cnt <= 28 && wide) return CALL(28, true);
+// Kernel instantiations.  Codes whose layers all have the same number of data links per check node
+// (every DVB-S2 normal-frame table) get the link count as a compile-time constant: no predication,
+// no dead link slots.  The rest take the predicated variant of the next size up.  The narrow state
+// word holds 15 sign bits (<= 13 data links), above that the wide (two-word) state is used.
+#define DVBS2_DISPATCH(CALL)                                              \
+    if (uniform) {                                                        \
+        switch (max_cnt) {                                                \
+        case 2: return CALL(2, true, false);                              \
+        case 3: return CALL(3, true, false);                              \
+        case 4: return CALL(4, true, false);                              \
+        case 5: return CALL(5, true, false);                              \
+        case 7: return CALL(7, true, false);                              \
+        case 8: return CALL(8, true, false);                              \
+        case 9: return CALL(9, true, false);                              \
+        case 11: return CALL(11, true, false);                            \
+        case 12: return CALL(12, true, false);                            \
+        case 16: return CALL(16, true, true);                             \
+        case 20: return CALL(20, true, true);                             \
+        case 25: return CALL(25, true, true);                             \
+        case 28: return CALL(28, true, true);                             \
+        default: break;                                                   \
+        }                                                                 \
+    }                                                                     \
+    if (max_cnt <= 5) return CALL(5, false, false);                       \
+    if (max_cnt <= 9) return CALL(9, false, false);                       \
+    if (max_cnt <= 13) return CALL(13, false, false);                     \
+    if (max_cnt <= 18) return CALL(18, false, true);                      \
+    if (max_cnt <= 28) return CALL(28, false, true);
 
-cudaError_t ldpc_launch(const LdpcLaunch& p, int max_cnt, bool wide, int grid, size_t smem, cudaStream_t stream)
+cudaError_t ldpc_launch(const LdpcLaunch& p, int max_cnt, bool uniform, int grid, size_t smem, cudaStream_t stream)
 {
-#define CALL(C, W) launch_one<C, W>(p, grid, smem, stream)
+#define CALL(C, U, W) launch_one<C, U, W>(p, grid, smem, stream)
     DVBS2_DISPATCH(CALL)
 #undef CALL
     return cudaErrorInvalidValue;
 }
 
-int ldpc_ctas_per_sm(int max_cnt, bool wide, size_t smem)
+int ldpc_ctas_per_sm(int max_cnt, bool uniform, size_t smem)
 {
-#define CALL(C, W) occupancy_one<C, W>(smem)
+#define CALL(C, U, W) occupancy_one<C, U, W>(smem)
     DVBS2_DISPATCH(CALL)
 #undef CALL
     return 0;
 }
+
+bool ldpc_wide_state(int max_cnt) { return max_cnt > 13; }
 
 } // namespace dvbs2b200
