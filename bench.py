@@ -175,20 +175,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- code tables: built on rank 0, ONE NCCL broadcast, every rank creates from the blob ----
-    if world > 1:
-        if rank == 0:
-            c0 = d.Code(d.STANDARD_DVBS2, d.FECFRAME_NORMAL, d.C1_2, device=local)
-            blob = torch.from_numpy(c0.export_tables()).to(dev)
-            size = torch.tensor([blob.numel()], device=dev, dtype=torch.int64)
-        else:
-            size = torch.zeros(1, device=dev, dtype=torch.int64)
-        dist.broadcast(size, 0)
-        if rank != 0:
-            blob = torch.empty(int(size.item()), device=dev, dtype=torch.uint8)
-        dist.broadcast(blob, 0)
-        code = c0 if rank == 0 else d.Code(device=local, tables=blob.cpu().numpy())
-    else:
-        code = d.Code(d.STANDARD_DVBS2, d.FECFRAME_NORMAL, d.C1_2, device=local)
+    from dvbs2rx_b200 import sharding
+    code = sharding.make_code(d.STANDARD_DVBS2, d.FECFRAME_NORMAL, d.C1_2, local)
     info = code.info
     F = FRAMES_PER_GPU
     N, nb, kb = info.n_ldpc, info.nbch // 8, info.kbch // 8

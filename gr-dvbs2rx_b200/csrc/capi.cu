@@ -402,6 +402,22 @@ int dvbs2b200_schedule_stats(int table, int* steps_per_iter, int* max_depth, int
     return DVBS2B200_OK;
 }
 
+int dvbs2b200_tables_build(int standard, int framesize, int rate, void* buf, size_t cap, size_t* size)
+{
+    std::vector<uint8_t> blob;
+    std::string err;
+    if (!build_blob(standard, framesize, rate, blob, err))
+        return fail(DVBS2B200_EUNSUPPORTED, err);
+    if (size)
+        *size = blob.size();
+    if (buf) {
+        if (cap < blob.size())
+            return fail(DVBS2B200_EINVAL, "buffer too small");
+        memcpy(buf, blob.data(), blob.size());
+    }
+    return DVBS2B200_OK;
+}
+
 int dvbs2b200_code_create(dvbs2b200_code** h, int device, int standard, int framesize, int rate)
 {
     if (!h)

@@ -59,6 +59,7 @@ _SIGS = {
     "dvbs2b200_table_circulants": (C.c_int, [C.c_int, _P, C.c_int]),
     "dvbs2b200_bch_genpoly": (C.c_int, [C.c_int, C.c_int, _P, C.c_int]),
     "dvbs2b200_schedule_stats": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "dvbs2b200_tables_build": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "dvbs2b200_code_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int]),
     "dvbs2b200_code_export_tables": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "dvbs2b200_code_create_from_tables": (C.c_int, [C.POINTER(_P), C.c_int, _P, C.c_size_t]),
@@ -129,6 +130,15 @@ def schedule_stats(table):
     a, b, c = C.c_int(), C.c_int(), C.c_int()
     _check(lib().dvbs2b200_schedule_stats(table, C.byref(a), C.byref(b), C.byref(c)))
     return dict(steps_per_iter=a.value, max_depth=b.value, conflict_layers=c.value)
+
+
+def build_tables(standard, framesize, rate):
+    """Packed code tables (uint8 array) built on the host; no device needed."""
+    size = C.c_size_t()
+    _check(lib().dvbs2b200_tables_build(standard, framesize, rate, None, 0, C.byref(size)))
+    buf = np.zeros(size.value, dtype=np.uint8)
+    _check(lib().dvbs2b200_tables_build(standard, framesize, rate, buf.ctypes.data, buf.size, C.byref(size)))
+    return buf
 
 
 def bits_per_symbol(constellation):

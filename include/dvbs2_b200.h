@@ -95,7 +95,10 @@ int dvbs2b200_schedule_stats(int table, int* steps_per_iter, int* max_depth, int
  * generator data), uploads them to `device`, creates the stream and staging buffers. */
 int dvbs2b200_code_create(dvbs2b200_code** h, int device, int standard, int framesize, int rate);
 /* The packed tables as one relocatable blob, so that rank 0 can build them once and
- * broadcast them (one ncclBroadcast through torch.distributed) to the other ranks. */
+ * broadcast them (one ncclBroadcast through torch.distributed) to the other ranks.
+ * dvbs2b200_tables_build is the host-only half of dvbs2b200_code_create (no device needed):
+ * call with buf == NULL to get the size. */
+int dvbs2b200_tables_build(int standard, int framesize, int rate, void* buf, size_t cap, size_t* size);
 int dvbs2b200_code_export_tables(const dvbs2b200_code* h, void* buf, size_t cap, size_t* size);
 int dvbs2b200_code_create_from_tables(dvbs2b200_code** h, int device, const void* blob, size_t size);
 void dvbs2b200_code_destroy(dvbs2b200_code* h);

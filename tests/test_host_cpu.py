@@ -1,0 +1,136 @@
+"""CPU tests of the host side: code lookup, schedule, table blob, C-ABI surface, vector generator,
+and the N > 1 sharding logic under gloo.  No compute call is made (no GPU here)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    import dvbs2rx_b200 as d
+    hdr = open(os.path.join(ROOT, "include", "dvbs2_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(dvbs2b200_\w+)\s*\(", hdr)))
+    assert declared == sorted(d.EXPORTED_SYMBOLS)
+    lib = C.CDLL(d.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert d.lib().dvbs2b200_version() == 100
+
+
+def test_lookup_matches_reference_parameters(built):
+    """lib/fec_params.cc / lib/ldpc_decoder_bb_impl.cc:104-307 spot checks (Appendix C of SURVEY.md)."""
+    import dvbs2rx_b200 as d
+    exp = {
+        ("C1_2", 1): ("DVB_S2_TABLE_B4", 64800, 32400, 90, 32208, 32400, 12, 16),
+        ("C3_4", 1): ("DVB_S2_TABLE_B7", 64800, 48600, 45, 48408, 48600, 12, 16),
+        ("C3_5", 1): ("DVB_S2_TABLE_B5", 64800, 38880, 72, 38688, 38880, 12, 16),
+        ("C2_3", 0): ("DVB_S2_TABLE_C6", 16200, 10800, 15, 10632, 10800, 12, 14),
+        ("C9_10", 1): ("DVB_S2_TABLE_B11", 64800, 58320, 18, 58192, 58320, 8, 16),
+    }
+    for (rate, fs), (name, n, k, q, kb, nb, t, m) in exp.items():
+        i = d.lookup(d.STANDARD_DVBS2, fs, d.RATE[rate])
+        assert d.lib().dvbs2b200_table_name(i.table).decode() == name
+        assert (i.n_ldpc, i.k_ldpc, i.q, i.kbch, i.nbch, i.t, i.gf_m) == (n, k, q, kb, nb, t, m)
+    # the standard selects the T2 table only for 2/3 normal and 3/5 short
+    assert d.lib().dvbs2b200_table_name(d.lookup(d.STANDARD_DVBT2, 1, d.C2_3).table) == b"DVB_T2_TABLE_A3"
+    assert d.lib().dvbs2b200_table_name(d.lookup(d.STANDARD_DVBT2, 0, d.C3_5).table) == b"DVB_T2_TABLE_B3"
+    with pytest.raises(d.Dvbs2Error) as e:
+        d.lookup(0, 1, d.C7_8)  # not a DVB-S2 rate (the reference leaves d_ldpc unset)
+    assert e.value.code == d.EUNSUPPORTED
+
+
+def test_circulants_reproduce_links_total(built):
+    import dvbs2rx_b200 as d
+    for table in range(d.lib().dvbs2b200_num_tables()):
+        layer, group, shift = d.table_circulants(table)
+        assert (shift < 360).all() and (np.diff(layer) >= 0).all()
+        # one circulant = 360 edges; a (layer, group) pair may repeat (conflict layers) but never a triple
+        assert len(set(zip(layer.tolist(), group.tolist(), shift.tolist()))) == len(layer)
+
+
+def test_schedule_statistics_match_survey(built):
+    """SURVEY.md Appendix C [probe]: wavefront steps per iteration / deepest layer / conflict layers."""
+    import dvbs2rx_b200 as d
+    exp = {("C1_2", 1): (162, 33, 8), ("C3_4", 1): (349, 180, 20), ("C3_5", 1): (293, 36, 30),
+           ("C2_3", 0): (160, 52, 11), ("C9_10", 1): (197, 90, 18)}
+    for (rate, fs), (steps, depth, conf) in exp.items():
+        s = d.schedule_stats(d.lookup(0, fs, d.RATE[rate]).table)
+        assert (s["steps_per_iter"], s["max_depth"], s["conflict_layers"]) == (steps, depth, conf)
+
+
+def test_wavefront_schedule_preserves_serial_order(built):
+    """Replay the device schedule on the host: every data bit must be touched by check nodes in the
+    same relative order as the reference's serial j loop (lib/ldpc_decoder/layered_decoder.hh:50-79)."""
+    import dvbs2rx_b200 as d
+    for rate, fs in (("C1_2", 1), ("C9_10", 1), ("C2_3", 0), ("C3_4", 1)):
+        table = d.lookup(0, fs, d.RATE[rate]).table
+        layer, group, shift = d.table_circulants(table)
+        for i in np.unique(layer):
+            circ = [(g, a) for l, g, a in zip(layer, group, shift) if l == i]
+            if len({g for g, _ in circ}) == len(circ):
+                continue
+            last = {}
+            level = np.zeros(360, dtype=int)
+            for j in range(360):
+                bits = [(g, (j - a) % 360) for g, a in circ]
+                level[j] = 1 + max([last.get(b, 0) for b in bits])
+                for b in bits:
+                    last[b] = level[j]
+            # same-level check nodes never share a bit; lower j never sits at a higher level than a
+            # later node that shares one of its bits
+            for lv in range(1, level.max() + 1):
+                seen = set()
+                for j in np.nonzero(level == lv)[0]:
+                    bits = {(g, (j - a) % 360) for g, a in circ}
+                    assert not (bits & seen)
+                    seen |= bits
+
+
+def test_compute_calls_fail_loudly_without_a_gpu(built):
+    import dvbs2rx_b200 as d
+    if d.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(d.Dvbs2Error) as e:
+        d.Code(d.STANDARD_DVBS2, d.FECFRAME_NORMAL, d.C1_2)
+    assert e.value.code == d.ECUDA and "no CPU fallback" in str(e.value)
+
+
+def test_vector_generator_roundtrips_through_the_oracle(oracle):
+    import dvbs2rx_b200 as d
+    from dvbs2rx_b200 import vectors
+    msg, cw, llr, info = vectors.make_llr_frames(0, 0, d.C2_3, 3, 6.0, seed=9)
+    post, ret = oracle.ldpc_decode(info.table, llr, 25)
+    hard = oracle.pack_hard(post, info.nbch)
+    out, corr = oracle.bch_decode(oracle.bch(0, info.t, info.nbch), hard)
+    assert (ret >= 0).all() and (corr >= 0).all()
+    assert np.array_equal(out, msg)
+    # 8PSK mapper / interleaver against the oracle demapper's hard decisions (no noise)
+    msg, cw, info = vectors.encode_frames(0, 1, d.C3_5, 1, np.random.default_rng(2))
+    iq = vectors.map_symbols(cw, d.MOD_8PSK, d.C3_5)
+    llr = oracle.demap_8psk(iq, 0.1, d.C3_5)
+    assert np.array_equal((llr < 0).astype(np.uint8), cw)
+    iq = vectors.map_symbols(cw, d.MOD_QPSK, d.C3_5)
+    assert np.array_equal((oracle.demap_qpsk(iq, 0.5) < 0).astype(np.uint8), cw)
+
+
+def test_sharding_under_gloo_world_size_2(built, tmp_path):
+    """N > 1 host logic on CPU: contiguous frame shards, table blob broadcast from rank 0, counters
+    all-reduced -- the same code path bench.py/run_sharded uses with NCCL."""
+    script = os.path.join(ROOT, "tests", "_gloo_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29541")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29541", script, str(tmp_path)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    outs = sorted(os.listdir(tmp_path))
+    assert outs == ["rank0.txt", "rank1.txt"]
+    a, b = (open(os.path.join(tmp_path, o)).read().split() for o in outs)
+    assert a[0] == b[0]            # same table blob digest on both ranks
+    assert (a[1], b[1]) == ("0:50", "50:100")  # contiguous shards of 100 frames
+    assert a[2] == b[2] == "100"   # all-reduced frame counter
