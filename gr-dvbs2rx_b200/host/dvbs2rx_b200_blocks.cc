@@ -1,0 +1,483 @@
+// dvbs2rx_b200_blocks.cc -- see dvbs2rx_b200_blocks.h.  Pure host C++ above include/dvbs2_b200.h.
+#include "dvbs2rx_b200_blocks.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <string>
+
+#include "../../include/dvbs2_b200.h"
+
+namespace gr {
+namespace dvbs2rx {
+
+namespace {
+dvbs2b200_code* create_code(int standard, int framesize, int rate)
+{
+    dvbs2b200_code* h = nullptr;
+    int rc = dvbs2b200_code_create(&h, 0, standard, framesize, rate);
+    if (rc != DVBS2B200_OK)
+        throw std::runtime_error(std::string("dvbs2b200: ") + dvbs2b200_last_error());
+    return h;
+}
+const int DEFAULT_TRIALS = 25; // lib/ldpc_decoder_bb_impl.cc:391
+} // namespace
+
+// ---- ldpc_decoder_bb ------------------------------------------------------------------------------
+ldpc_decoder_bb::sptr ldpc_decoder_bb::make(dvb_standard_t standard, dvb_framesize_t framesize, dvb_code_rate_t rate,
+                                            dvb_constellation_t /*constellation*/, dvb_outputmode_t outputmode,
+                                            dvb_infomode_t /*infomode*/, int max_trials, int /*debug_level*/)
+{
+    sptr b(new ldpc_decoder_bb());
+    b->d_code = create_code(standard, framesize, rate);
+    dvbs2b200_code_info info;
+    dvbs2b200_code_info_get(b->d_code, &info);
+    b->d_kldpc = info.nbch; // lib/ldpc_decoder_bb_impl.cc:97-102: kldpc = bch.n
+    b->d_nldpc = info.n_ldpc;
+    b->d_kldpc_bytes = b->d_kldpc / 8;
+    b->d_nldpc_bytes = b->d_nldpc / 8;
+    b->d_output_mode = outputmode;
+    b->d_max_trials = max_trials;
+    b->set_batches_per_call(1);
+    return b;
+}
+
+ldpc_decoder_bb::~ldpc_decoder_bb() { dvbs2b200_code_destroy(d_code); }
+
+void ldpc_decoder_bb::set_batches_per_call(int n)
+{
+    // lib/ldpc_decoder_bb_impl.cc:354-360 with simd -> n * 32 frames per scheduler call
+    const int frames = std::max(1, n) * d_simd_size;
+    if (d_output_mode == OM_MESSAGE) {
+        d_output_multiple = d_kldpc_bytes * frames;
+        d_relative_rate = (double)d_kldpc_bytes / d_nldpc;
+    } else {
+        d_output_multiple = d_nldpc_bytes * frames;
+        d_relative_rate = (double)d_nldpc_bytes / d_nldpc;
+    }
+}
+
+void ldpc_decoder_bb::forecast(int noutput_items, gr_vector_int& ninput_items_required)
+{
+    if (d_output_mode == OM_MESSAGE) { // lib/ldpc_decoder_bb_impl.cc:380-389
+        unsigned int n_frames = noutput_items / d_kldpc_bytes;
+        ninput_items_required[0] = n_frames * d_nldpc;
+    } else {
+        ninput_items_required[0] = 8 * noutput_items;
+    }
+}
+
+int ldpc_decoder_bb::general_work(int noutput_items, gr_vector_int& /*ninput_items*/,
+                                  gr_vector_const_void_star& input_items, gr_vector_void_star& output_items)
+{
+    const int8_t* in = (const int8_t*)input_items[0];
+    unsigned char* out = (unsigned char*)output_items[0];
+    const int trials = (d_max_trials == 0) ? DEFAULT_TRIALS : d_max_trials;
+    const int output_size = d_output_mode ? d_kldpc_bytes : d_nldpc_bytes;
+    const int frames = noutput_items / output_size; // a multiple of d_simd_size by the output multiple
+    if (frames <= 0 || frames % d_simd_size) {
+        d_consumed = 0;
+        return 0;
+    }
+    const bool want_pdu = (bool)d_pdu_handler;
+    if (want_pdu)
+        d_post.resize((size_t)frames * d_nldpc);
+    d_ret.resize(frames);
+    // one launch for the whole call; groups of 32 frames keep the reference's coupled iteration loop
+    int rc = dvbs2b200_ldpc_decode(d_code, in, frames, trials, d_simd_size, d_output_mode, out,
+                                   want_pdu ? d_post.data() : nullptr, d_ret.data());
+    if (rc != DVBS2B200_OK)
+        throw std::runtime_error(std::string("dvbs2b200_ldpc_decode: ") + dvbs2b200_last_error());
+    for (int b = 0; b < frames / d_simd_size; ++b) {
+        const int count = d_ret[(size_t)b * d_simd_size];
+        d_total_trials += (count < 0) ? trials : (trials - count); // lib/ldpc_decoder_bb_impl.cc:411-419
+        if (want_pdu) {
+            llr_pdu pdu;
+            pdu.simd_size = d_simd_size;
+            pdu.frame_cnt = d_frame_cnt;
+            pdu.llr = d_post.data() + (size_t)b * d_simd_size * d_nldpc;
+            pdu.n_llr = (size_t)d_simd_size * d_nldpc;
+            d_pdu_handler(pdu);
+        }
+        d_frame_cnt += d_simd_size;
+        d_batch_cnt++;
+    }
+    d_consumed = frames * d_nldpc; // consume_each
+    return frames * output_size;
+}
+
+// ---- bch_decoder_bb -------------------------------------------------------------------------------
+bch_decoder_bb::sptr bch_decoder_bb::make(dvb_standard_t standard, dvb_framesize_t framesize, dvb_code_rate_t rate,
+                                          dvb_outputmode_t /*outputmode*/, int /*debug_level*/)
+{
+    sptr b(new bch_decoder_bb());
+    b->d_code = create_code(standard, framesize, rate);
+    dvbs2b200_code_info info;
+    dvbs2b200_code_info_get(b->d_code, &info);
+    if (info.kbch % 8 || info.nbch % 8) // lib/bch.cc:19-24 assert_byte_aligned_n_k
+        throw std::runtime_error("u8 array messages are only supported for n and k multiple of 8.");
+    b->d_k_bytes = info.kbch / 8;
+    b->d_n_bytes = info.nbch / 8;
+    return b;
+}
+
+bch_decoder_bb::~bch_decoder_bb() { dvbs2b200_code_destroy(d_code); }
+
+void bch_decoder_bb::forecast(int noutput_items, gr_vector_int& ninput_items_required)
+{
+    ninput_items_required[0] = (noutput_items / d_k_bytes) * d_n_bytes; // lib/bch_decoder_bb_impl.cc:78-82
+}
+
+int bch_decoder_bb::general_work(int noutput_items, gr_vector_int& /*ninput_items*/,
+                                 gr_vector_const_void_star& input_items, gr_vector_void_star& output_items)
+{
+    const unsigned char* in = (const unsigned char*)input_items[0];
+    unsigned char* out = (unsigned char*)output_items[0];
+    const int n_codewords = noutput_items / d_k_bytes;
+    d_corr.resize(std::max(n_codewords, 1));
+    int rc = dvbs2b200_bch_decode(d_code, in, n_codewords, out, d_corr.data());
+    if (rc != DVBS2B200_OK)
+        throw std::runtime_error(std::string("dvbs2b200_bch_decode: ") + dvbs2b200_last_error());
+    for (int i = 0; i < n_codewords; i++) { // lib/bch_decoder_bb_impl.cc:94-111
+        if (d_corr[i] == -1)
+            d_frame_error_cnt++;
+        d_frame_cnt++;
+    }
+    d_consumed = n_codewords * d_n_bytes;
+    return noutput_items;
+}
+
+// ---- xfecframe_demapper_cb ------------------------------------------------------------------------
+xfecframe_demapper_cb::sptr xfecframe_demapper_cb::make(dvb_framesize_t framesize, dvb_code_rate_t rate,
+                                                        dvb_constellation_t constellation)
+{
+    sptr b(new xfecframe_demapper_cb());
+    b->d_constellation = constellation;
+    b->d_rate = rate;
+    if (framesize == FECFRAME_NORMAL)
+        b->d_fecframe_len = 64800;
+    else if (framesize == FECFRAME_MEDIUM)
+        b->d_fecframe_len = 32400;
+    else
+        b->d_fecframe_len = 16200;
+    if (constellation == MOD_QPSK) {
+        b->d_bits = 2;
+    } else if (constellation == MOD_8PSK) {
+        b->d_bits = 3;
+        unsigned int rows = b->d_fecframe_len / 3; // lib/xfecframe_demapper_cb_impl.cc:48-69
+        if (rate == C3_5) {
+            b->d_rowaddr0 = rows * 2, b->d_rowaddr1 = rows, b->d_rowaddr2 = 0;
+        } else if (rate == C25_36 || rate == C13_18 || rate == C7_15 || rate == C8_15 || rate == C26_45) {
+            b->d_rowaddr0 = rows, b->d_rowaddr1 = 0, b->d_rowaddr2 = rows * 2;
+        } else {
+            b->d_rowaddr0 = 0, b->d_rowaddr1 = rows, b->d_rowaddr2 = rows * 2;
+        }
+    } else {
+        throw std::runtime_error("Unsupported constellation");
+    }
+    b->d_xfecframe_len = b->d_fecframe_len / b->d_bits;
+    for (size_t i = 0; i < kPool; i++) {
+        b->d_saved[i] = std::numeric_limits<uint64_t>::max();
+        b->d_pool[i].resize(b->d_xfecframe_len);
+    }
+    b->d_code = create_code(STANDARD_DVBS2, framesize, rate);
+    return b;
+}
+
+xfecframe_demapper_cb::~xfecframe_demapper_cb() { dvbs2b200_code_destroy(d_code); }
+
+void xfecframe_demapper_cb::forecast(int noutput_items, gr_vector_int& ninput_items_required)
+{
+    ninput_items_required[0] = noutput_items / d_bits;
+}
+
+namespace {
+const float SQRT2_2 = 0.70710678118654752440f;
+// lib/psk.hh:135-141 hard + :152-157 map for 8PSK
+inline gr_complex slice_8psk(gr_complex c)
+{
+    static const gr_complex m_8psk[8] = { { SQRT2_2, SQRT2_2 }, { 1, 0 }, { -1, 0 }, { -SQRT2_2, -SQRT2_2 },
+                                          { 0, 1 }, { SQRT2_2, -SQRT2_2 }, { -SQRT2_2, SQRT2_2 }, { 0, -1 } };
+    const gr_complex rot((float)std::cos(-M_PI / 8), (float)std::sin(-M_PI / 8));
+    c *= rot;
+    int b1 = c.real() < 0, b2 = c.imag() < 0, b0 = std::abs(c.real()) < std::abs(c.imag());
+    return m_8psk[(b0 << 2) | (b1 << 1) | b2];
+}
+inline gr_complex map_8psk_bits(int b0, int b1, int b2)
+{
+    static const gr_complex m_8psk[8] = { { SQRT2_2, SQRT2_2 }, { 1, 0 }, { -1, 0 }, { -SQRT2_2, -SQRT2_2 },
+                                          { 0, 1 }, { SQRT2_2, -SQRT2_2 }, { -SQRT2_2, SQRT2_2 }, { 0, -1 } };
+    return m_8psk[(b0 << 2) | (b1 << 1) | b2];
+}
+} // namespace
+
+// lib/qpsk.h:240-244,41-65 (QPSK) / lib/xfecframe_demapper_cb_impl.cc:131-145 (8PSK): Es/N0 from hard slices
+float xfecframe_demapper_cb::estimate_snr_symbols(const gr_complex* in) const
+{
+    float sp = 0, np = 0;
+    for (unsigned int j = 0; j < d_xfecframe_len; j++) {
+        gr_complex s;
+        if (d_constellation == MOD_QPSK)
+            s = gr_complex(in[j].real() >= 0 ? SQRT2_2 : -SQRT2_2, in[j].imag() >= 0 ? SQRT2_2 : -SQRT2_2);
+        else
+            s = slice_8psk(in[j]);
+        sp += std::norm(s);
+        np += std::norm(in[j] - s);
+    }
+    if (!(np > 0))
+        np = 1e-12f;
+    return sp / np;
+}
+
+// post-decoder estimate: reference points rebuilt from the posterior LLR signs
+// (lib/qpsk.h:267-281; lib/xfecframe_demapper_cb_impl.cc:270-305 for 8PSK)
+float xfecframe_demapper_cb::estimate_snr_llr(const gr_complex* in, const int8_t* llr) const
+{
+    float sp = 0, np = 0;
+    for (unsigned int j = 0; j < d_xfecframe_len; j++) {
+        gr_complex s;
+        if (d_constellation == MOD_QPSK) {
+            s = gr_complex(llr[2 * j] >= 0 ? SQRT2_2 : -SQRT2_2, llr[2 * j + 1] >= 0 ? SQRT2_2 : -SQRT2_2);
+        } else {
+            s = map_8psk_bits(llr[d_rowaddr0 + j] < 0, llr[d_rowaddr1 + j] < 0, llr[d_rowaddr2 + j] < 0);
+        }
+        sp += std::norm(s);
+        np += std::norm(in[j] - s);
+    }
+    if (!(np > 0))
+        np = 1e-12f;
+    return sp / np;
+}
+
+int xfecframe_demapper_cb::general_work(int noutput_items, gr_vector_int& /*ninput_items*/,
+                                        gr_vector_const_void_star& input_items, gr_vector_void_star& output_items)
+{
+    std::lock_guard<std::mutex> l(d_mutex);
+    const gr_complex* in = static_cast<const gr_complex*>(input_items[0]);
+    int8_t* out = static_cast<int8_t*>(output_items[0]);
+    const int n_frames = noutput_items / d_fecframe_len;
+    d_n0_per_frame.resize(std::max(n_frames, 1));
+    const gr_complex* p = in;
+    for (int i = 0; i < n_frames; i++) { // lib/xfecframe_demapper_cb_impl.cc:115-149
+        d_saved[d_idx] = d_frame_cnt;
+        memcpy(d_pool[d_idx].data(), p, d_xfecframe_len * sizeof(gr_complex));
+        d_idx = (d_idx + 1) % kPool;
+        if (d_waiting_first_llr) {
+            float snr_lin = estimate_snr_symbols(p);
+            d_snr = 10 * std::log10(snr_lin);
+            d_N0 = 1.0f / snr_lin;
+            d_precision = 4.0 / d_N0;
+        }
+        d_n0_per_frame[i] = d_N0;
+        p += d_xfecframe_len;
+        d_frame_cnt++;
+    }
+    // soft demap + deinterleave of the whole call in one launch, N0 explicit per frame
+    int rc = dvbs2b200_demap(d_code, d_constellation, reinterpret_cast<const float*>(in), n_frames,
+                             d_n0_per_frame.data(), out);
+    if (rc != DVBS2B200_OK)
+        throw std::runtime_error(std::string("dvbs2b200_demap: ") + dvbs2b200_last_error());
+    d_consumed = n_frames * d_xfecframe_len;
+    return noutput_items;
+}
+
+void xfecframe_demapper_cb::handle_llr_pdu(const llr_pdu& pdu)
+{
+    std::lock_guard<std::mutex> l(d_mutex);
+    if (!pdu.llr || pdu.n_llr == 0 || pdu.n_llr != (size_t)pdu.simd_size * d_fecframe_len)
+        return; // the reference logs and drops malformed PDUs (:193-242)
+    size_t n_frames = pdu.n_llr / d_fecframe_len, n_processed = 0;
+    float accum = 0;
+    for (size_t i = 0; i < n_frames; i++) {
+        size_t idx = kPool;
+        for (size_t k = 0; k < kPool; k++)
+            if (d_saved[k] == pdu.frame_cnt + i) {
+                idx = k;
+                break;
+            }
+        if (idx == kPool)
+            continue;
+        accum += estimate_snr_llr(d_pool[idx].data(), pdu.llr + i * d_fecframe_len);
+        n_processed++;
+    }
+    float avg = accum / n_processed; // :312-317 (NaN when nothing was processed, as the reference)
+    d_snr = 10 * std::log10(avg);
+    d_N0 = 1.0f / avg;
+    d_precision = 4.0 / d_N0;
+    if (n_processed > 0)
+        d_waiting_first_llr = false;
+}
+
+} // namespace dvbs2rx
+} // namespace gr
+
+// ---- ldpc_cuda: the decode seam --------------------------------------------------------------------
+namespace ldpc_cuda {
+namespace {
+dvbs2b200_code* g_code = nullptr; // a process-wide singleton, like the reference's ISA decoders
+int g_simd = 32, g_n = 0;
+std::vector<int32_t> g_ret;
+} // namespace
+
+int ldpc_dec_init(int standard, int framesize, int rate, int simd_size)
+{
+    ldpc_dec_shutdown();
+    if (simd_size != 16 && simd_size != 32)
+        return DVBS2B200_EINVAL;
+    int rc = dvbs2b200_code_create(&g_code, 0, standard, framesize, rate);
+    if (rc != DVBS2B200_OK)
+        return rc;
+    dvbs2b200_code_info info;
+    dvbs2b200_code_info_get(g_code, &info);
+    g_n = info.n_ldpc;
+    g_simd = simd_size;
+    g_ret.resize(simd_size);
+    return DVBS2B200_OK;
+}
+
+int ldpc_dec_decode(void* /*buffer*/, int8_t* code, int trials)
+{
+    if (!g_code)
+        return -1;
+    // posteriors overwrite `code` in place; hard decisions are taken by the caller from them
+    int rc = dvbs2b200_ldpc_decode(g_code, code, g_simd, trials, g_simd, /*OM_CODEWORD*/ 0, nullptr, code, g_ret.data());
+    if (rc != DVBS2B200_OK)
+        return -1;
+    return g_ret[0];
+}
+
+void ldpc_dec_shutdown()
+{
+    if (g_code)
+        dvbs2b200_code_destroy(g_code);
+    g_code = nullptr;
+}
+} // namespace ldpc_cuda
+
+// ---- C hooks so the blocks can be driven from the Python parity tests (ctypes) ------------------------
+using namespace gr::dvbs2rx;
+extern "C" {
+
+struct blk_ldpc {
+    ldpc_decoder_bb::sptr b;
+    std::vector<int8_t> pdus;
+    std::vector<uint64_t> pdu_frames;
+};
+
+void* blk_ldpc_make(int standard, int framesize, int rate, int outputmode, int max_trials, int batches, int want_pdu)
+{
+    try {
+        blk_ldpc* h = new blk_ldpc();
+        h->b = ldpc_decoder_bb::make((dvb_standard_t)standard, (dvb_framesize_t)framesize, (dvb_code_rate_t)rate,
+                                     MOD_QPSK, (dvb_outputmode_t)outputmode, INFO_OFF, max_trials);
+        h->b->set_batches_per_call(batches);
+        if (want_pdu)
+            h->b->set_llr_pdu_handler([h](const llr_pdu& p) {
+                h->pdus.insert(h->pdus.end(), p.llr, p.llr + p.n_llr);
+                h->pdu_frames.push_back(p.frame_cnt);
+            });
+        return h;
+    } catch (...) {
+        return nullptr;
+    }
+}
+void blk_ldpc_free(void* h) { delete (blk_ldpc*)h; }
+int blk_ldpc_output_multiple(void* h) { return ((blk_ldpc*)h)->b->output_multiple(); }
+int blk_ldpc_forecast(void* h, int noutput_items)
+{
+    gr_vector_int req(1);
+    ((blk_ldpc*)h)->b->forecast(noutput_items, req);
+    return req[0];
+}
+int blk_ldpc_work(void* h, int noutput_items, const int8_t* in, int n_in, unsigned char* out, int* consumed)
+{
+    blk_ldpc* b = (blk_ldpc*)h;
+    gr_vector_int ninput(1, n_in);
+    gr_vector_const_void_star ins(1, in);
+    gr_vector_void_star outs(1, out);
+    try {
+        int r = b->b->general_work(noutput_items, ninput, ins, outs);
+        *consumed = b->b->consumed();
+        return r;
+    } catch (...) {
+        return -1000;
+    }
+}
+unsigned blk_ldpc_average_trials(void* h) { return ((blk_ldpc*)h)->b->get_average_trials(); }
+size_t blk_ldpc_pdu_bytes(void* h, int8_t* out, size_t cap)
+{
+    blk_ldpc* b = (blk_ldpc*)h;
+    if (out && cap >= b->pdus.size())
+        memcpy(out, b->pdus.data(), b->pdus.size());
+    return b->pdus.size();
+}
+
+void* blk_bch_make(int standard, int framesize, int rate)
+{
+    try {
+        auto* p = new bch_decoder_bb::sptr(
+            bch_decoder_bb::make((dvb_standard_t)standard, (dvb_framesize_t)framesize, (dvb_code_rate_t)rate, OM_MESSAGE));
+        return p;
+    } catch (...) {
+        return nullptr;
+    }
+}
+void blk_bch_free(void* h) { delete (bch_decoder_bb::sptr*)h; }
+int blk_bch_work(void* h, int noutput_items, const unsigned char* in, unsigned char* out, int* consumed)
+{
+    auto& b = *(bch_decoder_bb::sptr*)h;
+    gr_vector_int ninput(1, 0);
+    gr_vector_const_void_star ins(1, in);
+    gr_vector_void_star outs(1, out);
+    try {
+        int r = b->general_work(noutput_items, ninput, ins, outs);
+        *consumed = b->consumed();
+        return r;
+    } catch (...) {
+        return -1000;
+    }
+}
+uint64_t blk_bch_frame_count(void* h) { return (*(bch_decoder_bb::sptr*)h)->get_frame_count(); }
+uint64_t blk_bch_error_count(void* h) { return (*(bch_decoder_bb::sptr*)h)->get_error_count(); }
+
+void* blk_demap_make(int framesize, int rate, int constellation, char* err, int errcap)
+{
+    try {
+        return new xfecframe_demapper_cb::sptr(
+            xfecframe_demapper_cb::make((dvb_framesize_t)framesize, (dvb_code_rate_t)rate, (dvb_constellation_t)constellation));
+    } catch (const std::exception& e) {
+        if (err && errcap > 0) {
+            strncpy(err, e.what(), errcap - 1);
+            err[errcap - 1] = 0;
+        }
+        return nullptr;
+    }
+}
+void blk_demap_free(void* h) { delete (xfecframe_demapper_cb::sptr*)h; }
+int blk_demap_work(void* h, int noutput_items, const float* in, int8_t* out, int* consumed)
+{
+    auto& b = *(xfecframe_demapper_cb::sptr*)h;
+    gr_vector_int ninput(1, 0);
+    gr_vector_const_void_star ins(1, in);
+    gr_vector_void_star outs(1, out);
+    try {
+        int r = b->general_work(noutput_items, ninput, ins, outs);
+        *consumed = b->consumed();
+        return r;
+    } catch (...) {
+        return -1000;
+    }
+}
+float blk_demap_snr(void* h) { return (*(xfecframe_demapper_cb::sptr*)h)->get_snr(); }
+void blk_demap_llr_pdu(void* h, long simd, uint64_t frame_cnt, const int8_t* llr, size_t n)
+{
+    llr_pdu p{ simd, frame_cnt, llr, n };
+    (*(xfecframe_demapper_cb::sptr*)h)->handle_llr_pdu(p);
+}
+
+int blk_ldpc_cuda_init(int standard, int framesize, int rate, int simd) { return ldpc_cuda::ldpc_dec_init(standard, framesize, rate, simd); }
+int blk_ldpc_cuda_decode(int8_t* code, int trials) { return ldpc_cuda::ldpc_dec_decode(nullptr, code, trials); }
+void blk_ldpc_cuda_shutdown() { ldpc_cuda::ldpc_dec_shutdown(); }
+
+} // extern "C"

@@ -1,0 +1,158 @@
+// dvbs2rx_b200_blocks.h -- host-side mirror of the three gr-dvbs2rx blocks on the FEC decode path,
+// written above the C ABI of libdvbs2_b200.so.
+//
+// GNU Radio is not available in this build environment, so these classes do not derive from
+// gr::block; they keep the reference's class names, factory signatures, stream contracts
+// (item sizes, output multiples, relative rates, forecast), general_work argument meaning and
+// return values, counters and error behaviour, so that the body of each reference *_impl.cc can
+// be replaced by a call into them (INTEGRATION.md shows the patch):
+//   ldpc_decoder_bb        <- include/gnuradio/dvbs2rx/ldpc_decoder_bb.h:38-51, lib/ldpc_decoder_bb_impl.{h,cc}
+//   bch_decoder_bb         <- include/gnuradio/dvbs2rx/bch_decoder_bb.h:39-55,  lib/bch_decoder_bb_impl.{h,cc}
+//   xfecframe_demapper_cb  <- include/gnuradio/dvbs2rx/xfecframe_demapper_cb.h:36-44, lib/xfecframe_demapper_cb_impl.{h,cc}
+// and ldpc_cuda::ldpc_dec_init / ldpc_dec_decode, the pair that slots in beside the reference's ISA
+// namespaces (lib/ldpc_decoder_bb_impl.cc:34-52) behind `int (*decode)(void*, int8_t*, int)`.
+#pragma once
+#include <array>
+#include <complex>
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <vector>
+
+#include "dvb_config.h"
+
+struct dvbs2b200_code;
+
+typedef std::complex<float> gr_complex;
+typedef std::vector<int> gr_vector_int;
+typedef std::vector<const void*> gr_vector_const_void_star;
+typedef std::vector<void*> gr_vector_void_star;
+
+namespace gr {
+namespace dvbs2rx {
+
+// Frames handed to the GPU per launch by the LDPC block.  The reference's d_simd_size is 32 (AVX2);
+// a B200 wants thousands of frames in flight, so the block asks the scheduler for a multiple of the
+// reference's batch and keeps the reference's batch semantics inside it (term_group = 32).
+constexpr int kRefSimdSize = 32;
+
+// What the reference publishes on "llr_pdu" (lib/ldpc_decoder_bb_impl.cc:362-367,422-429):
+// meta {simd_size, frame_cnt} + posterior LLRs of one SIMD batch.
+struct llr_pdu {
+    long simd_size;
+    uint64_t frame_cnt;
+    const int8_t* llr; // [simd_size][n_ldpc]
+    size_t n_llr;
+};
+
+class ldpc_decoder_bb
+{
+public:
+    typedef std::shared_ptr<ldpc_decoder_bb> sptr;
+    static sptr make(dvb_standard_t standard, dvb_framesize_t framesize, dvb_code_rate_t rate,
+                     dvb_constellation_t constellation, dvb_outputmode_t outputmode, dvb_infomode_t infomode,
+                     int max_trials, int debug_level = 0);
+    ~ldpc_decoder_bb();
+
+    void forecast(int noutput_items, gr_vector_int& ninput_items_required);
+    int general_work(int noutput_items, gr_vector_int& ninput_items, gr_vector_const_void_star& input_items,
+                     gr_vector_void_star& output_items);
+    unsigned int get_average_trials() { return d_total_trials / d_batch_cnt; } // per batch, as the reference
+
+    // stream contract (what the reference passes to set_output_multiple / set_relative_rate)
+    int output_multiple() const { return d_output_multiple; }
+    double relative_rate() const { return d_relative_rate; }
+    int consumed() const { return d_consumed; } // what general_work passed to consume_each
+    // out-port "llr_pdu": called once per 32-frame batch, in order
+    void set_llr_pdu_handler(std::function<void(const llr_pdu&)> h) { d_pdu_handler = std::move(h); }
+    // frames per launch = batches_per_call * 32; 1 reproduces the reference's granularity
+    void set_batches_per_call(int n);
+
+private:
+    ldpc_decoder_bb() {}
+    dvbs2b200_code* d_code = nullptr;
+    unsigned int d_nldpc, d_nldpc_bytes, d_kldpc, d_kldpc_bytes, d_output_mode;
+    uint64_t d_frame_cnt = 0, d_batch_cnt = 0;
+    unsigned int d_total_trials = 0;
+    int d_max_trials;
+    int d_simd_size = kRefSimdSize;
+    int d_output_multiple = 0, d_consumed = 0;
+    double d_relative_rate = 0;
+    std::vector<int8_t> d_post;
+    std::vector<int32_t> d_ret;
+    std::function<void(const llr_pdu&)> d_pdu_handler;
+};
+
+class bch_decoder_bb
+{
+public:
+    typedef std::shared_ptr<bch_decoder_bb> sptr;
+    static sptr make(dvb_standard_t standard, dvb_framesize_t framesize, dvb_code_rate_t rate,
+                     dvb_outputmode_t outputmode, int debug_level = 0);
+    ~bch_decoder_bb();
+    void forecast(int noutput_items, gr_vector_int& ninput_items_required);
+    int general_work(int noutput_items, gr_vector_int& ninput_items, gr_vector_const_void_star& input_items,
+                     gr_vector_void_star& output_items);
+    uint64_t get_frame_count() { return d_frame_cnt; }
+    uint64_t get_error_count() { return d_frame_error_cnt; }
+    int output_multiple() const { return (int)d_k_bytes; }
+    int consumed() const { return d_consumed; }
+
+private:
+    bch_decoder_bb() {}
+    dvbs2b200_code* d_code = nullptr;
+    unsigned int d_k_bytes, d_n_bytes;
+    uint64_t d_frame_cnt = 0, d_frame_error_cnt = 0;
+    int d_consumed = 0;
+    std::vector<int32_t> d_corr;
+};
+
+class xfecframe_demapper_cb
+{
+public:
+    typedef std::shared_ptr<xfecframe_demapper_cb> sptr;
+    // throws std::runtime_error("Unsupported constellation") like lib/xfecframe_demapper_cb_impl.cc:70-72
+    static sptr make(dvb_framesize_t framesize, dvb_code_rate_t rate, dvb_constellation_t constellation);
+    ~xfecframe_demapper_cb();
+    void forecast(int noutput_items, gr_vector_int& ninput_items_required);
+    int general_work(int noutput_items, gr_vector_int& ninput_items, gr_vector_const_void_star& input_items,
+                     gr_vector_void_star& output_items);
+    // in-port "llr_pdu" (lib/xfecframe_demapper_cb_impl.cc:188-318)
+    void handle_llr_pdu(const llr_pdu& pdu);
+    float get_snr() { return d_snr; }
+    int output_multiple() const { return (int)d_fecframe_len; }
+    int consumed() const { return d_consumed; }
+
+private:
+    xfecframe_demapper_cb() {}
+    float estimate_snr_symbols(const gr_complex* in) const;
+    float estimate_snr_llr(const gr_complex* in, const int8_t* llr) const;
+    dvbs2b200_code* d_code = nullptr;
+    dvb_constellation_t d_constellation;
+    dvb_code_rate_t d_rate;
+    bool d_waiting_first_llr = true;
+    unsigned int d_fecframe_len, d_xfecframe_len, d_bits;
+    unsigned int d_rowaddr0 = 0, d_rowaddr1 = 0, d_rowaddr2 = 0;
+    float d_snr = 0, d_N0 = 1, d_precision = 4;
+    uint64_t d_frame_cnt = 0;
+    int d_consumed = 0;
+    std::mutex d_mutex;
+    static constexpr size_t kPool = 64; // XFECFRAME_POOL_SIZE
+    std::array<std::vector<gr_complex>, kPool> d_pool;
+    std::array<uint64_t, kPool> d_saved;
+    size_t d_idx = 0;
+    std::vector<float> d_n0_per_frame;
+};
+
+} // namespace dvbs2rx
+} // namespace gr
+
+// The seam of lib/ldpc_decoder_bb_impl.h:41: `code` is [simd][N] int8, overwritten with posterior
+// LLRs; returns trials left (>= 0) or -1; `buffer` (the ISA paths' scratch) is unused.
+namespace ldpc_cuda {
+int ldpc_dec_init(int standard, int framesize, int rate, int simd_size);
+int ldpc_dec_decode(void* buffer, int8_t* code, int trials);
+void ldpc_dec_shutdown();
+} // namespace ldpc_cuda
