@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -134,6 +135,11 @@ int create_from_blob(dvbs2b200_code** out, int device, std::vector<uint8_t>&& bl
     h->ldpc_smem = ldpc_smem_bytes(h->hdr.N, h->hdr.smem_bytes, nullptr);
     if (h->hdr.max_cnt <= 28 && h->ldpc_smem <= (size_t)h->smem_optin)
         h->ldpc_ctas = ldpc_ctas_per_sm(h->hdr.max_cnt, h->hdr.uniform_cnt != 0, h->ldpc_smem);
+    if (const char* cap = getenv("DVBS2B200_LDPC_CTAS_PER_SM")) { // tuning knob: cap the resident CTAs per SM
+        int c = atoi(cap);
+        if (c > 0 && c < h->ldpc_ctas)
+            h->ldpc_ctas = c;
+    }
     *out = h;
     return DVBS2B200_OK;
 }

@@ -98,6 +98,43 @@ void build_schedule(const LdpcTableDef& def, Schedule& s)
         s.steps_per_iter += depth;
         s.max_depth = std::max(s.max_depth, depth);
     }
+
+    // ---- barrier placement ---------------------------------------------------------------------
+    // dirty_all / dirty_w0: groups written since the last block barrier by steps every warp runs /
+    // by warp-0-only steps.  Group index ngroups stands for "parity bits touched across threads".
+    std::vector<char> dirty_all(ngroups + 1, 0), dirty_w0(ngroups + 1, 0);
+    auto clear = [&]() {
+        std::fill(dirty_all.begin(), dirty_all.end(), 0);
+        std::fill(dirty_w0.begin(), dirty_w0.end(), 0);
+    };
+    for (size_t k = 0; k < s.steps.size(); ++k) {
+        StepRec& st = s.steps[k];
+        const bool conflict_layer = st.count != 0;
+        const bool w0 = conflict_layer && st.count <= 32;
+        std::vector<int> groups;
+        for (auto& ga : per_layer[st.layer])
+            groups.push_back(ga.first);
+        // conflict layers run single check nodes on arbitrary threads: their parity links are not
+        // thread private, and the neighbouring layers' parity links collide with them
+        const bool prev_conflict = k > 0 && s.steps[k - 1].count != 0;
+        bool need = false;
+        for (int g : groups)
+            need |= dirty_all[g] || (!w0 && dirty_w0[g]);
+        if (conflict_layer || prev_conflict) // cross-thread parity access: every earlier step wrote parity
+            need |= dirty_all[ngroups] || (!w0 && dirty_w0[ngroups]);
+        groups.push_back(ngroups); // every step writes parity bits
+        if (k == 0)
+            need = false; // the iteration starts behind a barrier
+        if (need) {
+            st.work_off |= kStepBarrierBefore;
+            s.barriers_per_iter++;
+            clear();
+        }
+        if (w0)
+            st.work_off |= kStepWarp0;
+        for (int g : groups)
+            (w0 ? dirty_w0 : dirty_all)[g] = 1;
+    }
 }
 
 // ---- GF(2^m) ---------------------------------------------------------------------------------

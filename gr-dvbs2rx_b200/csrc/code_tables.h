@@ -29,7 +29,7 @@ const ModcodDef* find_modcod(int standard, int framesize, int rate);
 
 // ---- packed blob ---------------------------------------------------------------------------
 constexpr uint32_t kBlobMagic = 0x32425344u; // "DSB2"
-constexpr uint32_t kBlobVersion = 5;
+constexpr uint32_t kBlobVersion = 6;
 
 // One per layer, 8 bytes, lives in shared memory.
 struct LayerRec {
@@ -48,8 +48,15 @@ struct EdgeRec {
 struct StepRec {
     uint16_t layer;
     uint16_t count;
-    uint32_t work_off;
+    uint32_t work_off; // low 24 bits: offset into work[]; high bits: kStep* flags
 };
+// A block barrier is needed before a step only if it touches a 360-bit group (or parity bits) that
+// another thread wrote since the last barrier; consecutive conflict-free layers over disjoint groups
+// run without one (parity links are thread private there).  Wavefront steps of at most 32 check
+// nodes are run by warp 0 alone, ordered by __syncwarp() instead of block barriers.
+constexpr uint32_t kStepBarrierBefore = 1u << 24;
+constexpr uint32_t kStepWarp0 = 1u << 25;
+constexpr uint32_t kStepOffMask = (1u << 24) - 1;
 
 struct BlobHeader {
     uint32_t magic, version, total_bytes, reserved0;
@@ -101,7 +108,7 @@ struct Schedule {
     std::vector<EdgeRec> edges;
     std::vector<StepRec> steps; // one iteration, in execution order
     std::vector<uint16_t> order; // work[]: check-node indices of the conflict steps
-    int max_cnt = 0, min_cnt = 1 << 30, steps_per_iter = 0, max_depth = 0, conflict_layers = 0;
+    int max_cnt = 0, min_cnt = 1 << 30, steps_per_iter = 0, max_depth = 0, conflict_layers = 0, barriers_per_iter = 0;
 };
 void build_schedule(const LdpcTableDef& def, Schedule& s);
 

@@ -524,7 +524,8 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
             prefetch(st);
             for (int s = 0; s < p.n_steps; ++s) {
                 const int layer = (int)(st.x & 0xffffu), count = (int)(st.x >> 16);
-                const uint32_t work_off = st.y;
+                const uint32_t work_off = st.y & 0x00ffffffu;
+                const bool barrier_before = (st.y >> 24) & 1u, warp0_only = (st.y >> 25) & 1u;
                 const LayerView lv = load_layer(layers, layer);
                 const bool last = (s == p.n_steps - 1);
                 const uint32_t cA = wA, cB = wB, csA = sA, csB = sB;
@@ -532,6 +533,9 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
                     st = steps[s + 1];
                     prefetch(st); // the next layer's state words travel while this layer computes
                 }
+                // a block barrier only where another thread's writes are read (code_tables.cc)
+                if (barrier_before)
+                    __syncthreads();
                 if (count == 0) {
                     if (tid < kPairs) {
                         uint32_t* mo = msg + ((size_t)layer * kPairs + tid) * 2 * MW;
@@ -540,7 +544,9 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
                         else
                             process_pair<CNT_MAX, UNIFORM, WIDE, false>(L, edges, lv, layer, tid, K, q, cA, cB, csA, csB, mo, pol_keep);
                     }
-                } else {
+                } else if (!warp0_only || tid < 32) {
+                    // wavefront step of a conflict layer: single check nodes; narrow steps (<= 32 nodes)
+                    // run on warp 0 alone and are ordered by __syncwarp()
                     for (int t = tid; t < count; t += kLdpcThreads) {
                         const int j = (int)work[work_off + t];
                         const int pp = j >= kPairs ? j - kPairs : j;
@@ -550,12 +556,11 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
                         else
                             process_cn<CNT_MAX, UNIFORM, WIDE, false>(L, edges, lv, layer, j, K, q, mp, zero_state, pol_keep);
                     }
+                    if (warp0_only)
+                        __syncwarp();
                 }
-                if (last)
-                    proven_bad = __syncthreads_or(self_bad);
-                else
-                    __syncthreads();
             }
+            proven_bad = __syncthreads_or(self_bad);
         }
 
         // ---- outputs -----------------------------------------------------------------------------------
