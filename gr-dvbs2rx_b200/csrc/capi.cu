@@ -72,7 +72,8 @@ struct dvbs2b200_code {
     int device = 0;
     int sm_count = 0;
     int smem_optin = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;                    // compute (and default staging) stream
+    cudaStream_t s_in = nullptr, s_out = nullptr;     // copy streams of the pipelined host path
     std::vector<uint8_t> blob;
     BlobHeader hdr;
     uint8_t* d_blob = nullptr;
@@ -126,7 +127,9 @@ int create_from_blob(dvbs2b200_code** out, int device, std::vector<uint8_t>&& bl
         return bail(fail(DVBS2B200_ECUDA, "cudaSetDevice failed"));
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess)
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking)) != cudaSuccess)
         return bail(cuda_fail(e, "cudaStreamCreate"));
     if ((e = cudaMalloc((void**)&h->d_blob, h->blob.size())) != cudaSuccess)
         return bail(cuda_fail(e, "cudaMalloc(tables)"));
@@ -470,8 +473,9 @@ void dvbs2b200_code_destroy(dvbs2b200_code* h)
         b->release();
     if (h->d_blob)
         cudaFree(h->d_blob);
-    if (h->stream)
-        cudaStreamDestroy(h->stream);
+    for (cudaStream_t st : { h->stream, h->s_in, h->s_out })
+        if (st)
+            cudaStreamDestroy(st);
     delete h;
 }
 
@@ -618,6 +622,40 @@ int dvbs2b200_demap(dvbs2b200_code* h, int constellation, const float* iq, int f
 }
 
 // ---- fused chain ------------------------------------------------------------------------------
+} // extern "C"
+
+namespace {
+// demap -> LDPC -> BCH on frames [f0, f0 + nf) of a batch whose buffers hold `frames` frames
+int fec_dev_range(dvbs2b200_code* h, int constellation, const float* d_iq, const float* d_n0, const int8_t* d_llr,
+                  int f0, int nf, int max_trials, int term_group, uint8_t* d_llr_scratch, uint8_t* d_mid,
+                  uint8_t* d_msg, int32_t* d_trials_left, int32_t* d_corrections, cudaStream_t s)
+{
+    const BlobHeader& hd = h->hdr;
+    int rc;
+    const int8_t* llr = nullptr;
+    if (d_iq) {
+        const int bits = bits_per_symbol(constellation);
+        if (!bits)
+            return fail(DVBS2B200_EUNSUPPORTED, "Unsupported constellation");
+        int8_t* out = (int8_t*)d_llr_scratch + (size_t)f0 * hd.N;
+        if ((rc = demap_dev(h, constellation, d_iq + (size_t)f0 * (hd.N / bits) * 2, nf, d_n0 + f0, out, s)))
+            return rc;
+        llr = out;
+    } else {
+        llr = d_llr + (size_t)f0 * hd.N;
+    }
+    const int mid_stride = hd.kldpc_out / 8; // OM_MESSAGE: BCH codeword bytes
+    uint8_t* mid = d_mid + (size_t)f0 * mid_stride;
+    if ((rc = ldpc_dev(h, llr, nf, max_trials, term_group, /*OM_MESSAGE*/ 1, mid, nullptr,
+                       d_trials_left ? d_trials_left + f0 : nullptr, s)))
+        return rc;
+    return bch_dev(h, mid, mid_stride, nf, d_msg + (size_t)f0 * (hd.kbch / 8),
+                   d_corrections ? d_corrections + f0 : nullptr, s);
+}
+} // namespace
+
+extern "C" {
+
 int dvbs2b200_fec_decode_dev(dvbs2b200_code* h, int constellation, const float* d_iq, const float* d_n0,
                              const int8_t* d_llr, int frames, int max_trials, int term_group, uint8_t* d_msg,
                              int32_t* d_trials_left, int32_t* d_corrections, void* stream)
@@ -630,24 +668,17 @@ int dvbs2b200_fec_decode_dev(dvbs2b200_code* h, int constellation, const float* 
         return DVBS2B200_OK;
     if (!d_msg || (!d_iq && !d_llr))
         return fail(DVBS2B200_EINVAL, "null buffer");
+    if (d_iq && !d_n0)
+        return fail(DVBS2B200_EINVAL, "n0 is null");
     DeviceGuard g(h->device);
     const BlobHeader& hd = h->hdr;
-    cudaStream_t s = (cudaStream_t)stream;
     int rc;
-    if (d_iq) {
-        if ((rc = h->d_llr.ensure((size_t)frames * hd.N)))
-            return rc;
-        if ((rc = demap_dev(h, constellation, d_iq, frames, d_n0, (int8_t*)h->d_llr.p, s)))
-            return rc;
-        d_llr = (const int8_t*)h->d_llr.p;
-    }
-    const int mid_stride = hd.kldpc_out / 8; // OM_MESSAGE: BCH codeword bytes
-    if ((rc = h->d_mid.ensure((size_t)frames * mid_stride)))
+    if (d_iq && (rc = h->d_llr.ensure((size_t)frames * hd.N)))
         return rc;
-    if ((rc = ldpc_dev(h, d_llr, frames, max_trials, term_group, /*OM_MESSAGE*/ 1, (uint8_t*)h->d_mid.p, nullptr,
-                       d_trials_left, s)))
+    if ((rc = h->d_mid.ensure((size_t)frames * (hd.kldpc_out / 8))))
         return rc;
-    return bch_dev(h, (const uint8_t*)h->d_mid.p, mid_stride, frames, d_msg, d_corrections, s);
+    return fec_dev_range(h, constellation, d_iq, d_n0, d_llr, 0, frames, max_trials, term_group, (uint8_t*)h->d_llr.p,
+                         (uint8_t*)h->d_mid.p, d_msg, d_trials_left, d_corrections, (cudaStream_t)stream);
 }
 
 int dvbs2b200_fec_decode(dvbs2b200_code* h, int constellation, const float* iq, const float* n0, const int8_t* llr,
@@ -666,42 +697,82 @@ int dvbs2b200_fec_decode(dvbs2b200_code* h, int constellation, const float* iq, 
         return fail(DVBS2B200_EINVAL, "n0 is null");
     DeviceGuard g(h->device);
     const BlobHeader& hd = h->hdr;
-    cudaStream_t s = h->stream;
+    const int bits = iq ? bits_per_symbol(constellation) : 0;
+    if (iq && !bits)
+        return fail(DVBS2B200_EUNSUPPORTED, "Unsupported constellation");
+    if (term_group != 0 && term_group != 1 && term_group != 16 && term_group != 32)
+        return fail(DVBS2B200_EINVAL, "term_group must be 0, 16 or 32");
+    if (term_group > 1 && frames % term_group)
+        return fail(DVBS2B200_EINVAL, "frames must be a multiple of term_group");
+    const size_t in_stride = iq ? (size_t)(hd.N / bits) * 8 : (size_t)hd.N; // bytes per frame of input
+    const size_t out_stride = hd.kbch / 8;
     int rc;
-    const float* d_iq = nullptr;
-    const float* d_n0 = nullptr;
-    const int8_t* d_llr = nullptr;
-    if (iq) {
-        const int bits = bits_per_symbol(constellation);
-        if (!bits)
-            return fail(DVBS2B200_EUNSUPPORTED, "Unsupported constellation");
-        const size_t iq_bytes = (size_t)frames * (hd.N / bits) * 8;
-        if ((rc = h->d_in.ensure(iq_bytes)) || (rc = h->d_n0.ensure((size_t)frames * 4)))
-            return rc;
-        CU(cudaMemcpyAsync(h->d_in.p, iq, iq_bytes, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(h->d_n0.p, n0, (size_t)frames * 4, cudaMemcpyHostToDevice, s));
-        d_iq = (const float*)h->d_in.p;
-        d_n0 = (const float*)h->d_n0.p;
-    } else {
-        if ((rc = h->d_in.ensure((size_t)frames * hd.N)))
-            return rc;
-        CU(cudaMemcpyAsync(h->d_in.p, llr, (size_t)frames * hd.N, cudaMemcpyHostToDevice, s));
-        d_llr = (const int8_t*)h->d_in.p;
+    if ((rc = h->d_in.ensure((size_t)frames * in_stride)) || (rc = h->d_out.ensure((size_t)frames * out_stride)) ||
+        (rc = h->d_i32a.ensure((size_t)frames * 4)) || (rc = h->d_i32b.ensure((size_t)frames * 4)) ||
+        (rc = h->d_mid.ensure((size_t)frames * (hd.kldpc_out / 8))))
+        return rc;
+    if (iq && ((rc = h->d_n0.ensure((size_t)frames * 4)) || (rc = h->d_llr.ensure((size_t)frames * hd.N))))
+        return rc;
+    // Pipeline: the batch is cut into chunks of one full wave of resident CTAs; chunk c+1 is copied in
+    // (copy-in stream) and chunk c-1 copied out (copy-out stream) while chunk c computes.
+    int chunk = std::max(1, h->sm_count * std::max(1, h->ldpc_ctas));
+    if (term_group > 1)
+        chunk = std::max(term_group, chunk / term_group * term_group);
+    const int n_chunks = (frames + chunk - 1) / chunk;
+    std::vector<cudaEvent_t> ev_in(n_chunks, nullptr), ev_done(n_chunks, nullptr);
+    auto cleanup = [&]() {
+        for (cudaEvent_t e : ev_in)
+            if (e)
+                cudaEventDestroy(e);
+        for (cudaEvent_t e : ev_done)
+            if (e)
+                cudaEventDestroy(e);
+    };
+#define CUP(call)                                \
+    do {                                         \
+        cudaError_t e__ = (call);                \
+        if (e__ != cudaSuccess) {                \
+            cudaDeviceSynchronize();             \
+            cleanup();                           \
+            return cuda_fail(e__, #call);        \
+        }                                        \
+    } while (0)
+    if (iq)
+        CUP(cudaMemcpyAsync(h->d_n0.p, n0, (size_t)frames * 4, cudaMemcpyHostToDevice, h->s_in));
+    const uint8_t* src = iq ? (const uint8_t*)iq : (const uint8_t*)llr;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int f0 = c * chunk, nf = std::min(chunk, frames - f0);
+        CUP(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
+        CUP(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
+        CUP(cudaMemcpyAsync((uint8_t*)h->d_in.p + (size_t)f0 * in_stride, src + (size_t)f0 * in_stride,
+                            (size_t)nf * in_stride, cudaMemcpyHostToDevice, h->s_in));
+        CUP(cudaEventRecord(ev_in[c], h->s_in));
     }
-    const size_t out_bytes = (size_t)frames * (hd.kbch / 8);
-    if ((rc = h->d_out.ensure(out_bytes)) || (rc = h->d_i32a.ensure((size_t)frames * 4)) ||
-        (rc = h->d_i32b.ensure((size_t)frames * 4)))
-        return rc;
-    rc = dvbs2b200_fec_decode_dev(h, constellation, d_iq, d_n0, d_llr, frames, max_trials, term_group,
-                                  (uint8_t*)h->d_out.p, (int32_t*)h->d_i32a.p, (int32_t*)h->d_i32b.p, s);
-    if (rc)
-        return rc;
-    CU(cudaMemcpyAsync(msg, h->d_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
-    if (trials_left)
-        CU(cudaMemcpyAsync(trials_left, h->d_i32a.p, (size_t)frames * 4, cudaMemcpyDeviceToHost, s));
-    if (corrections)
-        CU(cudaMemcpyAsync(corrections, h->d_i32b.p, (size_t)frames * 4, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
+    for (int c = 0; c < n_chunks; ++c) {
+        const int f0 = c * chunk, nf = std::min(chunk, frames - f0);
+        CUP(cudaStreamWaitEvent(h->stream, ev_in[c], 0));
+        rc = fec_dev_range(h, constellation, iq ? (const float*)h->d_in.p : nullptr, (const float*)h->d_n0.p,
+                           iq ? nullptr : (const int8_t*)h->d_in.p, f0, nf, max_trials, term_group, (uint8_t*)h->d_llr.p,
+                           (uint8_t*)h->d_mid.p, (uint8_t*)h->d_out.p, (int32_t*)h->d_i32a.p, (int32_t*)h->d_i32b.p,
+                           h->stream);
+        if (rc) {
+            cudaDeviceSynchronize();
+            cleanup();
+            return rc;
+        }
+        CUP(cudaEventRecord(ev_done[c], h->stream));
+        CUP(cudaStreamWaitEvent(h->s_out, ev_done[c], 0));
+        CUP(cudaMemcpyAsync(msg + (size_t)f0 * out_stride, (uint8_t*)h->d_out.p + (size_t)f0 * out_stride,
+                            (size_t)nf * out_stride, cudaMemcpyDeviceToHost, h->s_out));
+        if (trials_left)
+            CUP(cudaMemcpyAsync(trials_left + f0, (int32_t*)h->d_i32a.p + f0, (size_t)nf * 4, cudaMemcpyDeviceToHost, h->s_out));
+        if (corrections)
+            CUP(cudaMemcpyAsync(corrections + f0, (int32_t*)h->d_i32b.p + f0, (size_t)nf * 4, cudaMemcpyDeviceToHost, h->s_out));
+    }
+    CUP(cudaStreamSynchronize(h->s_out));
+    CUP(cudaStreamSynchronize(h->stream));
+#undef CUP
+    cleanup();
     return DVBS2B200_OK;
 }
 
