@@ -64,7 +64,8 @@ void build_schedule(const LdpcTableDef& def, Schedule& s)
         L.conflict = conflict ? 1 : 0;
         if (!conflict) {
             StepRec st;
-            st.layer = (uint16_t)i;
+            st.layer = (uint8_t)i;
+            st.run_len = 0;
             st.count = 0;
             st.work_off = 0;
             s.steps.push_back(st);
@@ -87,7 +88,8 @@ void build_schedule(const LdpcTableDef& def, Schedule& s)
         }
         for (int lv = 1; lv <= depth; ++lv) {
             StepRec st;
-            st.layer = (uint16_t)i;
+            st.layer = (uint8_t)i;
+            st.run_len = 0;
             st.work_off = (uint32_t)s.order.size();
             for (int j = 0; j < 360; ++j)
                 if (level[j] == lv)
@@ -100,17 +102,57 @@ void build_schedule(const LdpcTableDef& def, Schedule& s)
     }
 
     // ---- barrier placement ---------------------------------------------------------------------
-    // dirty_all / dirty_w0: groups written since the last block barrier by steps every warp runs /
-    // by warp-0-only steps.  Group index ngroups stands for "parity bits touched across threads".
-    std::vector<char> dirty_all(ngroups + 1, 0), dirty_w0(ngroups + 1, 0);
+    // dirty_all / dirty_sub: groups written since the last block barrier by steps every warp runs /
+    // by link-parallel runs (a subset of the warps).  Group index ngroups stands for "parity bits touched across threads".
+    std::vector<char> dirty_all(ngroups + 1, 0), dirty_sub(ngroups + 1, 0);
     auto clear = [&]() {
         std::fill(dirty_all.begin(), dirty_all.end(), 0);
-        std::fill(dirty_w0.begin(), dirty_w0.end(), 0);
+        std::fill(dirty_sub.begin(), dirty_sub.end(), 0);
     };
+    auto group_lanes = [&](int layer) { // lanes per check node in the link-parallel path
+        const int deg = (int)per_layer[layer].size() + 2;
+        return deg <= 8 ? 8 : deg <= 16 ? 16 : 32;
+    };
+    // class of a wavefront step: 0 wide (all warps), 1 narrow scalar on warp 0, 2 link parallel.
+    // Instruction cost model (measured on B200): a scalar check-node update is ~55 warp instructions
+    // per link for up to 32 nodes, a link-parallel pass ~150 per warp of (node, link) lanes.
+    auto step_class = [&](const StepRec& st) {
+        if (st.count == 0 || st.count > 32)
+            return 0;
+        const int G = group_lanes(st.layer), deg = (int)per_layer[st.layer].size() + 2;
+        const int lp_warps = ((int)st.count * G + 31) / 32;
+        if (lp_warps <= 6 && 150 * lp_warps < 55 * deg)
+            return 2;
+        // high-degree codes (> 16 links): a scalar level is a ~1600-instruction dependent chain on one
+        // warp; spreading it over the links pays up to 14 nodes per level even with several passes
+        if (G == 32 && st.count <= 14)
+            return 2;
+        return 1;
+    };
+    // runs of consecutive narrow steps of one layer and one class
+    for (size_t k = 0; k < s.steps.size();) {
+        const int cls = step_class(s.steps[k]);
+        if (cls == 0) {
+            ++k;
+            continue;
+        }
+        size_t e = k;
+        int lanes = 0;
+        while (e < s.steps.size() && e - k < 255 && s.steps[e].layer == s.steps[k].layer && step_class(s.steps[e]) == cls) {
+            lanes = std::max(lanes, (int)s.steps[e].count * group_lanes(s.steps[e].layer));
+            ++e;
+        }
+        const int warps = cls == 2 ? std::min(6, (lanes + 31) / 32) : 1;
+        s.steps[k].run_len = (uint8_t)(e - k);
+        for (size_t t = k; t < e; ++t)
+            s.steps[t].work_off |= kStepRun | ((uint32_t)warps << kStepWarpsShift) | (cls == 2 ? kStepLinkParallel : 0u);
+        k = e;
+    }
     for (size_t k = 0; k < s.steps.size(); ++k) {
         StepRec& st = s.steps[k];
         const bool conflict_layer = st.count != 0;
-        const bool w0 = conflict_layer && st.count <= 32;
+        const bool sub = (st.work_off & kStepRun) != 0; // runs on a subset of the warps
+        const bool inside_run = sub && st.run_len == 0;          // ordered by the run's own barrier
         std::vector<int> groups;
         for (auto& ga : per_layer[st.layer])
             groups.push_back(ga.first);
@@ -119,21 +161,21 @@ void build_schedule(const LdpcTableDef& def, Schedule& s)
         const bool prev_conflict = k > 0 && s.steps[k - 1].count != 0;
         bool need = false;
         for (int g : groups)
-            need |= dirty_all[g] || (!w0 && dirty_w0[g]);
+            need |= dirty_all[g] || (!inside_run && dirty_sub[g]);
         if (conflict_layer || prev_conflict) // cross-thread parity access: every earlier step wrote parity
-            need |= dirty_all[ngroups] || (!w0 && dirty_w0[ngroups]);
+            need |= dirty_all[ngroups] || (!inside_run && dirty_sub[ngroups]);
         groups.push_back(ngroups); // every step writes parity bits
         if (k == 0)
             need = false; // the iteration starts behind a barrier
+        if (inside_run)
+            need = false; // (dirty_all was cleared by the barrier in front of the run)
         if (need) {
             st.work_off |= kStepBarrierBefore;
             s.barriers_per_iter++;
             clear();
         }
-        if (w0)
-            st.work_off |= kStepWarp0;
         for (int g : groups)
-            (w0 ? dirty_w0 : dirty_all)[g] = 1;
+            (sub ? dirty_sub : dirty_all)[g] = 1;
     }
 }
 

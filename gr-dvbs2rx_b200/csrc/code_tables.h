@@ -29,7 +29,7 @@ const ModcodDef* find_modcod(int standard, int framesize, int rate);
 
 // ---- packed blob ---------------------------------------------------------------------------
 constexpr uint32_t kBlobMagic = 0x32425344u; // "DSB2"
-constexpr uint32_t kBlobVersion = 6;
+constexpr uint32_t kBlobVersion = 8;
 
 // One per layer, 8 bytes, lives in shared memory.
 struct LayerRec {
@@ -43,19 +43,29 @@ struct EdgeRec {
     uint32_t e1; // PRMT selectors for p >= a': unpack | pack << 16
 };
 // One per schedule step of an iteration, 8 bytes, lives in shared memory.  A conflict-free layer
-// is one step (count == 0: check-node pair p = thread); a conflict layer is a run of wavefront
+// is one step (count == 0: check-node pair p = thread); a conflict layer is a sequence of wavefront
 // steps, each a list of `count` check-node indices j in work[work_off ...].
 struct StepRec {
-    uint16_t layer;
+    uint8_t layer;
+    uint8_t run_len;   // > 0 on the first step of a link-parallel run: steps in the run
     uint16_t count;
     uint32_t work_off; // low 24 bits: offset into work[]; high bits: kStep* flags
 };
-// A block barrier is needed before a step only if it touches a 360-bit group (or parity bits) that
-// another thread wrote since the last barrier; consecutive conflict-free layers over disjoint groups
-// run without one (parity links are thread private there).  Wavefront steps of at most 32 check
-// nodes are run by warp 0 alone, ordered by __syncwarp() instead of block barriers.
+// Barriers.  A block barrier is needed before a step only if it touches a 360-bit group (or parity
+// bits) that another thread wrote since the last barrier; consecutive conflict-free layers over
+// disjoint groups run without one (parity links are thread private there).
+// Wavefront steps come in three classes, chosen by instruction cost (code_tables.cc):
+//  * wide levels (> 32 check nodes): one check node per thread on all warps;
+//  * narrow levels: one check node per lane on warp 0 alone;
+//  * narrow levels of high-degree codes / long chains: "link parallel", one lane per (check node,
+//    link) with G = degree rounded up to 8/16/32 lanes per node, minima by warp REDUX, on the first
+//    nwarps warps.
+// Consecutive narrow levels of a layer form a run: the warps that take part order the levels with
+// __syncwarp() / a named barrier, the other warps skip the whole run.
 constexpr uint32_t kStepBarrierBefore = 1u << 24;
-constexpr uint32_t kStepWarp0 = 1u << 25;
+constexpr uint32_t kStepRun = 1u << 25;          // part of a run executed by a subset of the warps
+constexpr uint32_t kStepWarpsShift = 26;         // 3 bits: warps taking part in the run
+constexpr uint32_t kStepLinkParallel = 1u << 29; // run class: link parallel (else one node per lane)
 constexpr uint32_t kStepOffMask = (1u << 24) - 1;
 
 struct BlobHeader {

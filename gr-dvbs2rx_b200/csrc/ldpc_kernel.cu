@@ -294,13 +294,16 @@ __device__ __forceinline__ int process_pair(int8_t* __restrict__ L, const uint2*
 // ---- one check node j of a conflict layer (scalar, same arithmetic) -------------------------------
 template <int CNT_MAX, bool UNIFORM, bool WIDE, bool SELF_CHECK>
 __device__ __forceinline__ int process_cn(int8_t* __restrict__ L, const uint2* __restrict__ edges, const LayerView& lv, int layer,
-                                          int j, int K, int q, uint32_t* __restrict__ msg_pair, bool zero_state, uint64_t pol)
+                                          int j, int K, int q, uint32_t* __restrict__ msg_pair, bool zero_state, uint64_t pol,
+                                          bool have_state, uint32_t pw, uint32_t psg)
 {
     constexpr int DEG_MAX = CNT_MAX + 2;
     const int hsel = j >= kPairs; // which node of the pair
     const int half = kPairs * q;
     uint32_t w = 0, sg = 0;
-    if (!zero_state) {
+    if (have_state) {
+        w = pw, sg = psg;
+    } else if (!zero_state) {
         w = ldg_hint(msg_pair + hsel, pol);
         sg = WIDE ? ldg_hint(msg_pair + 2 + hsel, pol) : (w >> 17);
     }
@@ -373,6 +376,182 @@ __device__ __forceinline__ int process_cn(int8_t* __restrict__ L, const uint2* _
     if (SELF_CHECK)
         return (syn < 0) | zer;
     return 0;
+}
+
+// ---- link-parallel run: narrow wavefront levels of a conflict layer ----------------------------------
+// One lane per (check node, link): G = 8/16/32 lanes per check node, minima and sign parity by warp
+// REDUX over the group, sign bits by ballot.  The dependent chain through a deep conflict layer (up to
+// 180 levels for DVB-S2 3/4) then costs ~70 instructions per level on 1..6 warps instead of a full
+// scalar check-node update, and the levels are ordered by a named barrier among the warps that take part.
+__device__ __forceinline__ void sub_barrier(int nwarps)
+{
+    if (nwarps == 1)
+        __syncwarp();
+    else
+        asm volatile("bar.sync 1, %0;" ::"r"(nwarps * 32) : "memory");
+}
+
+template <bool WIDE>
+__device__ __noinline__ int lp_run(int8_t* __restrict__ L, const uint2* __restrict__ edges, const uint2* __restrict__ steps,
+                                   const uint16_t* __restrict__ work, uint32_t* __restrict__ msg, int cnt, uint32_t edge_begin,
+                                   int layer, int s0, int run_len, int nwarps, int last_step, int K, int q, bool zero_state,
+                                   uint64_t pol, int tid)
+{
+    constexpr int MW = WIDE ? 2 : 1;
+    const int deg = cnt + 2;
+    const int gshift = deg <= 8 ? 3 : deg <= 16 ? 4 : 5;
+    const int G = 1 << gshift;
+    const int link = tid & (G - 1);
+    const int lane = tid & 31;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+    const int nthreads = nwarps * 32;
+    const int half = kPairs * q;
+    const bool data_link = link >= 2 && link - 2 < cnt;
+    int ap = 0, ra = 0, gbase = 0;
+    if (data_link) {
+        const uint2 e = edges[edge_begin + link - 2];
+        ap = (int)(e.x >> 16);
+        ra = (int)(e.y & 1u);
+        gbase = (int)(e.x & 0xffffu) - 360 + 2 * ap;
+    }
+    int self_bad = 0;
+    // The check node of a lane's first item and its state word are fetched one level ahead (the index
+    // two levels ahead), so the L2 latency of the state is off the dependent chain through the layer.
+    auto load_j = [&](int k) -> int {
+        if (k >= run_len)
+            return -1;
+        const uint2 st = steps[s0 + k];
+        return ((tid >> gshift) < (int)(st.x >> 16)) ? (int)work[(st.y & 0x00ffffffu) + (tid >> gshift)] : -1;
+    };
+    auto load_state = [&](int j, uint32_t& w, uint32_t& sg) {
+        w = 0, sg = 0;
+        if (j >= 0 && !zero_state) {
+            const int hsel = j >= kPairs;
+            const uint32_t* mp = msg + ((size_t)layer * kPairs + (j - kPairs * hsel)) * 2 * MW;
+            w = ldg_hint(mp + hsel, pol);
+            sg = WIDE ? ldg_hint(mp + 2 + hsel, pol) : (w >> 17);
+        }
+    };
+    int j_cur = load_j(0), j_nxt = load_j(1);
+    uint32_t w_cur, sg_cur, w_nxt = 0, sg_nxt = 0;
+    load_state(j_cur, w_cur, sg_cur);
+    for (int k = 0; k < run_len; ++k) {
+        const uint2 st = steps[s0 + k];
+        const int count = (int)(st.x >> 16);
+        const uint32_t work_off = st.y & 0x00ffffffu;
+        const bool self_check = (s0 + k == last_step);
+        load_state(j_nxt, w_nxt, sg_nxt);
+        const int j_nn = load_j(k + 2);
+        for (int item = tid; (item >> gshift) < count; item += nthreads) {
+            int j;
+            uint32_t w, sg;
+            if (item == tid) {
+                j = j_cur, w = w_cur, sg = sg_cur;
+            } else {
+                j = (int)work[work_off + (item >> gshift)];
+                load_state(j, w, sg);
+            }
+            const int hsel = j >= kPairs;
+            const int pp = j - kPairs * hsel;
+            uint32_t* mp = msg + ((size_t)layer * kPairs + pp) * 2 * MW;
+            const int c = q * j + layer;
+            bool live;
+            int adr;
+            if (link == 0) {
+                live = true;
+                adr = parity_addr(K, half, c);
+            } else if (link == 1) {
+                live = c > 0;
+                adr = parity_addr(K, half, live ? c - 1 : 0);
+            } else {
+                live = data_link;
+                int sidx = j - ap - kPairs * ra;
+                sidx += (sidx < 0) ? 360 : 0;
+                adr = data_link ? data_addr(gbase, sidx) : 0;
+            }
+            int x = 0, key = 0x7fffffff;
+            if (live) {
+                const int l = (int)L[adr];
+                const int mc = (link == (int)((w >> 12) & 31u)) ? (int)((w >> 6) & 63u) : (int)(w & 63u);
+                const int old = ((sg >> link) & 1u) ? -mc : min(mc, 31);
+                x = min(max(l - old, -128), 127);
+                key = max(min(abs(x), 127) - 1, 0) * 32 + link;
+            }
+            const int k0 = __reduce_min_sync(gmask, key);
+            const int k1 = __reduce_min_sync(gmask, key == k0 ? 0x7fffffff : key);
+            const unsigned sx = __reduce_xor_sync(gmask, (unsigned)x);
+            const int min0 = k0 >> 5, min1 = k1 >> 5, arg = k0 & 31;
+            const int m = (link == arg) ? min1 : min0;
+            const bool neg = (int)(sx ^ (unsigned)x) < 0;
+            const int nl = min(max(x + (neg ? -m : m), -128), 127);
+            if (live)
+                L[adr] = (int8_t)nl;
+            const unsigned signs = __ballot_sync(gmask, live && neg) >> (lane & ~(G - 1));
+            if (link == 0) {
+                const uint32_t lo = (uint32_t)min(min0, 32) | ((uint32_t)min(min1, 32) << 6) | ((uint32_t)arg << 12);
+                if (!WIDE) {
+                    stg_hint(mp + hsel, lo | (signs << 17), pol);
+                } else {
+                    stg_hint(mp + hsel, lo, pol);
+                    stg_hint(mp + 2 + hsel, signs, pol);
+                }
+            }
+            if (self_check) {
+                const unsigned syn = __reduce_xor_sync(gmask, live ? (unsigned)nl : 0u);
+                const unsigned zero = __ballot_sync(gmask, live && nl == 0);
+                self_bad |= ((int)syn < 0) | (zero != 0);
+            }
+        }
+        sub_barrier(nwarps); // this level's writes are visible to the next level's lanes
+        j_cur = j_nxt, w_cur = w_nxt, sg_cur = sg_nxt;
+        j_nxt = j_nn;
+    }
+    return self_bad;
+}
+
+// ---- run of narrow wavefront levels on warp 0, one check node per lane, ordered by __syncwarp() -------
+template <int CNT_MAX, bool UNIFORM, bool WIDE>
+__device__ __noinline__ int scalar_run(int8_t* __restrict__ L, const uint2* __restrict__ edges, const uint2* __restrict__ steps,
+                                       const uint16_t* __restrict__ work, uint32_t* __restrict__ msg, const LayerView lv, int layer,
+                                       int s0, int run_len, int last_step, int K, int q, bool zero_state, uint64_t pol, int tid)
+{
+    constexpr int MW = WIDE ? 2 : 1;
+    int self_bad = 0;
+    // this lane's check node and its state word are fetched one level ahead
+    auto load_j = [&](int k) -> int {
+        if (k >= run_len)
+            return -1;
+        const uint2 st = steps[s0 + k];
+        return (tid < (int)(st.x >> 16)) ? (int)work[(st.y & 0x00ffffffu) + tid] : -1;
+    };
+    auto load_state = [&](int j, uint32_t& w, uint32_t& sg) {
+        w = 0, sg = 0;
+        if (j >= 0 && !zero_state) {
+            const int hsel = j >= kPairs;
+            const uint32_t* mp = msg + ((size_t)layer * kPairs + (j - kPairs * hsel)) * 2 * MW;
+            w = ldg_hint(mp + hsel, pol);
+            sg = WIDE ? ldg_hint(mp + 2 + hsel, pol) : (w >> 17);
+        }
+    };
+    int j_cur = load_j(0), j_nxt = load_j(1);
+    uint32_t w_cur, sg_cur, w_nxt = 0, sg_nxt = 0;
+    load_state(j_cur, w_cur, sg_cur);
+    for (int k = 0; k < run_len; ++k) {
+        load_state(j_nxt, w_nxt, sg_nxt);
+        const int j_nn = load_j(k + 2);
+        if (j_cur >= 0) {
+            const int pp = j_cur >= kPairs ? j_cur - kPairs : j_cur;
+            uint32_t* mp = msg + ((size_t)layer * kPairs + pp) * 2 * MW;
+            if (s0 + k == last_step)
+                self_bad |= process_cn<CNT_MAX, UNIFORM, WIDE, true>(L, edges, lv, layer, j_cur, K, q, mp, zero_state, pol, true, w_cur, sg_cur);
+            else
+                process_cn<CNT_MAX, UNIFORM, WIDE, false>(L, edges, lv, layer, j_cur, K, q, mp, zero_state, pol, true, w_cur, sg_cur);
+        }
+        __syncwarp();
+        j_cur = j_nxt, w_cur = w_nxt, sg_cur = sg_nxt;
+        j_nxt = j_nn;
+    }
+    return self_bad;
 }
 
 // lib/ldpc_decoder/layered_decoder.hh:32-49 for the pair (p, p+180): unsatisfied if the sign product
@@ -506,12 +685,11 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
 
             // ---- one iteration: walk the step list ---------------------------------------------------
             int self_bad = 0;
-            uint2 st = steps[0];
             uint32_t wA = 0, wB = 0, sA = 0, sB = 0;
-            // state words of a pair step, fetched one step ahead of their use
+            // state words of a pair step, requested from L2 one step ahead of their use
             auto prefetch = [&](uint2 s) {
                 if ((s.x >> 16) == 0 && tid < kPairs && !zero_state) {
-                    const uint32_t* m = msg + ((size_t)(s.x & 0xffffu) * kPairs + tid) * 2 * MW;
+                    const uint32_t* m = msg + ((size_t)(s.x & 0xffu) * kPairs + tid) * 2 * MW;
                     if (!WIDE) {
                         const uint2 t = ldg_hint(reinterpret_cast<const uint2*>(m), pol_keep);
                         wA = t.x, wB = t.y;
@@ -521,17 +699,21 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
                     }
                 }
             };
+            uint2 st = steps[0];
             prefetch(st);
-            for (int s = 0; s < p.n_steps; ++s) {
-                const int layer = (int)(st.x & 0xffffu), count = (int)(st.x >> 16);
+            const int last_step = p.n_steps - 1;
+            for (int s = 0; s < p.n_steps;) {
+                const int layer = (int)(st.x & 0xffu), run_len = (int)((st.x >> 8) & 0xffu), count = (int)(st.x >> 16);
                 const uint32_t work_off = st.y & 0x00ffffffu;
-                const bool barrier_before = (st.y >> 24) & 1u, warp0_only = (st.y >> 25) & 1u;
+                const bool barrier_before = (st.y >> 24) & 1u, is_run = (st.y >> 25) & 1u, link_parallel = (st.y >> 29) & 1u;
+                const int sub_warps = (int)((st.y >> 26) & 7u);
                 const LayerView lv = load_layer(layers, layer);
-                const bool last = (s == p.n_steps - 1);
+                const int next = s + (is_run ? run_len : 1);
+                const bool last = (next == p.n_steps);
                 const uint32_t cA = wA, cB = wB, csA = sA, csB = sB;
                 if (!last) {
-                    st = steps[s + 1];
-                    prefetch(st); // the next layer's state words travel while this layer computes
+                    st = steps[next];
+                    prefetch(st); // the next layer's state words travel while this one computes
                 }
                 // a block barrier only where another thread's writes are read (code_tables.cc)
                 if (barrier_before)
@@ -544,21 +726,29 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
                         else
                             process_pair<CNT_MAX, UNIFORM, WIDE, false>(L, edges, lv, layer, tid, K, q, cA, cB, csA, csB, mo, pol_keep);
                     }
-                } else if (!warp0_only || tid < 32) {
-                    // wavefront step of a conflict layer: single check nodes; narrow steps (<= 32 nodes)
-                    // run on warp 0 alone and are ordered by __syncwarp()
+                } else if (is_run) {
+                    // run of narrow wavefront levels on the first sub_warps warps; the other warps move on
+                    if (tid < sub_warps * 32) {
+                        if (link_parallel)
+                            self_bad |= lp_run<WIDE>(L, edges, steps, work, msg, lv.cnt, lv.edge_begin, layer, s, run_len, sub_warps,
+                                                     last_step, K, q, zero_state, pol_keep, tid);
+                        else
+                            self_bad |= scalar_run<CNT_MAX, UNIFORM, WIDE>(L, edges, steps, work, msg, lv, layer, s, run_len, last_step,
+                                                                          K, q, zero_state, pol_keep, tid);
+                    }
+                } else {
+                    // wide wavefront level: single check nodes, one per thread
                     for (int t = tid; t < count; t += kLdpcThreads) {
                         const int j = (int)work[work_off + t];
                         const int pp = j >= kPairs ? j - kPairs : j;
                         uint32_t* mp = msg + ((size_t)layer * kPairs + pp) * 2 * MW;
                         if (last)
-                            self_bad |= process_cn<CNT_MAX, UNIFORM, WIDE, true>(L, edges, lv, layer, j, K, q, mp, zero_state, pol_keep);
+                            self_bad |= process_cn<CNT_MAX, UNIFORM, WIDE, true>(L, edges, lv, layer, j, K, q, mp, zero_state, pol_keep, false, 0, 0);
                         else
-                            process_cn<CNT_MAX, UNIFORM, WIDE, false>(L, edges, lv, layer, j, K, q, mp, zero_state, pol_keep);
+                            process_cn<CNT_MAX, UNIFORM, WIDE, false>(L, edges, lv, layer, j, K, q, mp, zero_state, pol_keep, false, 0, 0);
                     }
-                    if (warp0_only)
-                        __syncwarp();
                 }
+                s = next;
             }
             proven_bad = __syncthreads_or(self_bad);
         }
