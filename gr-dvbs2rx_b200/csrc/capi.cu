@@ -81,7 +81,7 @@ struct dvbs2b200_code {
     int ldpc_ctas = 0; // resident LDPC CTAs per SM
     uint64_t launches = 0;
     // staging for the host-pointer entry points
-    DevBuf d_in, d_mid, d_out, d_post, d_i32a, d_i32b, d_n0, d_llr, d_sync, d_scratch;
+    DevBuf d_in, d_mid, d_out, d_post, d_i32a, d_i32b, d_n0, d_llr, d_sync, d_scratch, d_flag;
 };
 
 namespace {
@@ -177,7 +177,8 @@ int ldpc_grid(const dvbs2b200_code* h, int frames, int group)
 }
 
 int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials, int term_group, int output_mode,
-             uint8_t* d_hard, int8_t* d_llr_post, int32_t* d_trials_left, cudaStream_t stream)
+             uint8_t* d_hard, int8_t* d_llr_post, int32_t* d_trials_left, cudaStream_t stream,
+             const unsigned int* d_ready = nullptr, int ready_chunk = 0)
 {
     const BlobHeader& hd = h->hdr;
     if (frames < 0 || max_trials < 0)
@@ -221,6 +222,8 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
         p.msg_scratch = (uint32_t*)h->d_scratch.p;
     }
     p.llr = d_llr;
+    p.ready = d_ready;
+    p.ready_chunk = ready_chunk;
     p.frames = frames;
     p.max_trials = max_trials;
     p.group = group;
@@ -469,7 +472,7 @@ void dvbs2b200_code_destroy(dvbs2b200_code* h)
     DeviceGuard g(h->device);
     if (h->stream)
         cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : { &h->d_in, &h->d_mid, &h->d_out, &h->d_post, &h->d_i32a, &h->d_i32b, &h->d_n0, &h->d_llr, &h->d_sync, &h->d_scratch })
+    for (DevBuf* b : { &h->d_in, &h->d_mid, &h->d_out, &h->d_post, &h->d_i32a, &h->d_i32b, &h->d_n0, &h->d_llr, &h->d_sync, &h->d_scratch, &h->d_flag })
         b->release();
     if (h->d_blob)
         cudaFree(h->d_blob);
@@ -628,7 +631,8 @@ namespace {
 // demap -> LDPC -> BCH on frames [f0, f0 + nf) of a batch whose buffers hold `frames` frames
 int fec_dev_range(dvbs2b200_code* h, int constellation, const float* d_iq, const float* d_n0, const int8_t* d_llr,
                   int f0, int nf, int max_trials, int term_group, uint8_t* d_llr_scratch, uint8_t* d_mid,
-                  uint8_t* d_msg, int32_t* d_trials_left, int32_t* d_corrections, cudaStream_t s)
+                  uint8_t* d_msg, int32_t* d_trials_left, int32_t* d_corrections, cudaStream_t s,
+                  const unsigned int* d_ready = nullptr, int ready_chunk = 0)
 {
     const BlobHeader& hd = h->hdr;
     int rc;
@@ -647,7 +651,7 @@ int fec_dev_range(dvbs2b200_code* h, int constellation, const float* d_iq, const
     const int mid_stride = hd.kldpc_out / 8; // OM_MESSAGE: BCH codeword bytes
     uint8_t* mid = d_mid + (size_t)f0 * mid_stride;
     if ((rc = ldpc_dev(h, llr, nf, max_trials, term_group, /*OM_MESSAGE*/ 1, mid, nullptr,
-                       d_trials_left ? d_trials_left + f0 : nullptr, s)))
+                       d_trials_left ? d_trials_left + f0 : nullptr, s, d_ready, ready_chunk)))
         return rc;
     return bch_dev(h, mid, mid_stride, nf, d_msg + (size_t)f0 * (hd.kbch / 8),
                    d_corrections ? d_corrections + f0 : nullptr, s);
@@ -713,9 +717,63 @@ int dvbs2b200_fec_decode(dvbs2b200_code* h, int constellation, const float* iq, 
         return rc;
     if (iq && ((rc = h->d_n0.ensure((size_t)frames * 4)) || (rc = h->d_llr.ensure((size_t)frames * hd.N))))
         return rc;
-    // Pipeline: the batch is cut into chunks of one full wave of resident CTAs; chunk c+1 is copied in
-    // (copy-in stream) and chunk c-1 copied out (copy-out stream) while chunk c computes.
-    int chunk = std::max(1, h->sm_count * std::max(1, h->ldpc_ctas));
+    if (!iq && term_group <= 1) {
+        // Streaming path (LLR input): ONE persistent LDPC launch over the whole batch.  The input is
+        // copied in chunks on the copy-in stream, each followed by a one-thread kernel that bumps an
+        // arrival counter; a CTA waits on that counter before it loads a frame.  Host->device transfer
+        // and decoding overlap without cutting the batch into separate launches.
+        const int sc = std::max(32, h->sm_count); // frames per arrival flag
+        const int n_sc = (frames + sc - 1) / sc;
+        if ((rc = h->d_flag.ensure(16)))
+            return rc;
+        cudaEvent_t ev_zero = nullptr;
+        cudaError_t e;
+        unsigned int* flag = (unsigned int*)h->d_flag.p;
+        auto bail = [&](cudaError_t err, const char* what) {
+            cudaDeviceSynchronize();
+            if (ev_zero)
+                cudaEventDestroy(ev_zero);
+            return cuda_fail(err, what);
+        };
+        if ((e = cudaMemsetAsync(flag, 0, 4, h->s_in)) != cudaSuccess)
+            return bail(e, "cudaMemsetAsync(flag)");
+        if ((e = cudaEventCreateWithFlags(&ev_zero, cudaEventDisableTiming)) != cudaSuccess)
+            return bail(e, "cudaEventCreate");
+        if ((e = cudaEventRecord(ev_zero, h->s_in)) != cudaSuccess)
+            return bail(e, "cudaEventRecord");
+        for (int c = 0; c < n_sc; ++c) {
+            const int f0 = c * sc, nf = std::min(sc, frames - f0);
+            if ((e = cudaMemcpyAsync((uint8_t*)h->d_in.p + (size_t)f0 * in_stride, (const uint8_t*)llr + (size_t)f0 * in_stride,
+                                     (size_t)nf * in_stride, cudaMemcpyHostToDevice, h->s_in)) != cudaSuccess)
+                return bail(e, "cudaMemcpyAsync(llr chunk)");
+            if ((e = flag_launch(flag, (unsigned int)(c + 1), h->s_in)) != cudaSuccess)
+                return bail(e, "flag_launch");
+        }
+        if ((e = cudaStreamWaitEvent(h->stream, ev_zero, 0)) != cudaSuccess)
+            return bail(e, "cudaStreamWaitEvent");
+        rc = fec_dev_range(h, constellation, nullptr, nullptr, (const int8_t*)h->d_in.p, 0, frames, max_trials, term_group,
+                           (uint8_t*)h->d_llr.p, (uint8_t*)h->d_mid.p, (uint8_t*)h->d_out.p, (int32_t*)h->d_i32a.p,
+                           (int32_t*)h->d_i32b.p, h->stream, flag, sc);
+        if (rc) {
+            cudaDeviceSynchronize();
+            cudaEventDestroy(ev_zero);
+            return rc;
+        }
+        if ((e = cudaMemcpyAsync(msg, h->d_out.p, (size_t)frames * out_stride, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess)
+            return bail(e, "cudaMemcpyAsync(msg)");
+        if (trials_left && (e = cudaMemcpyAsync(trials_left, h->d_i32a.p, (size_t)frames * 4, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess)
+            return bail(e, "cudaMemcpyAsync(trials)");
+        if (corrections && (e = cudaMemcpyAsync(corrections, h->d_i32b.p, (size_t)frames * 4, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess)
+            return bail(e, "cudaMemcpyAsync(corrections)");
+        if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess)
+            return bail(e, "cudaStreamSynchronize");
+        if ((e = cudaStreamSynchronize(h->s_in)) != cudaSuccess)
+            return bail(e, "cudaStreamSynchronize");
+        cudaEventDestroy(ev_zero);
+        return DVBS2B200_OK;
+    }
+    // Pipeline (symbol input / group mode): the batch is cut into chunks of full waves of resident CTAs; chunk c+1 is copied in
+    int chunk = std::max(1, h->sm_count * std::max(1, h->ldpc_ctas)) * 2;
     if (term_group > 1)
         chunk = std::max(term_group, chunk / term_group * term_group);
     const int n_chunks = (frames + chunk - 1) / chunk;

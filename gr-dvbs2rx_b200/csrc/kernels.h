@@ -20,6 +20,9 @@ struct LdpcLaunch {
     uint32_t* msg_scratch;
     // batch
     const int8_t* llr; // [frames][N], 4-byte aligned
+    // streaming input: *ready counts the chunks of ready_chunk frames that have arrived (null: all there)
+    const unsigned int* ready;
+    int ready_chunk;
     int frames;
     int max_trials;
     int group;           // 0 per-frame termination, else frames per coupled group
@@ -61,5 +64,8 @@ struct DemapLaunch {
     int row0, row1, row2; // 8PSK deinterleaver row offsets
 };
 cudaError_t demap_launch(const DemapLaunch& p, cudaStream_t stream);
+
+// one-thread kernel that publishes `value` at *flag (stream-ordered after the copies before it)
+cudaError_t flag_launch(unsigned int* flag, unsigned int value, cudaStream_t stream);
 
 } // namespace dvbs2b200

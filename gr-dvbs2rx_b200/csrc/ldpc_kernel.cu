@@ -619,6 +619,16 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
     mbar_wait(bar, 0);
 
     for (int f = blockIdx.x; f < p.frames; f += gridDim.x) {
+        // ---- streaming input: wait until the host->device copy of this frame's chunk has landed ----
+        if (p.ready) {
+            if (tid == 0) {
+                const unsigned int need = (unsigned int)(f / p.ready_chunk) + 1u;
+                while (*reinterpret_cast<const volatile unsigned int*>(p.ready) < need)
+                    __nanosleep(500);
+                __threadfence();
+            }
+            __syncthreads();
+        }
         // ---- soft input: HBM -> shared memory, into the pair-interleaved order --------------------
         {
             const uint32_t* src = reinterpret_cast<const uint32_t*>(p.llr + (size_t)f * N);
@@ -828,6 +838,20 @@ int occupancy_one(size_t smem)
 }
 
 } // namespace
+
+namespace {
+__global__ void flag_kernel(unsigned int* flag, unsigned int value)
+{
+    __threadfence();
+    *reinterpret_cast<volatile unsigned int*>(flag) = value;
+}
+} // namespace
+
+cudaError_t flag_launch(unsigned int* flag, unsigned int value, cudaStream_t stream)
+{
+    flag_kernel<<<1, 1, 0, stream>>>(flag, value);
+    return cudaGetLastError();
+}
 
 size_t ldpc_smem_bytes(int N, uint32_t tab_bytes, LdpcLaunch* p)
 {
