@@ -87,6 +87,15 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 }
 // 0xFFFF in every half whose bit 15 is set
 __device__ __forceinline__ uint32_t signmask(uint32_t x) { return prmt(x, 0, 0xBB99); }
+// bitwise select: mask ? a : b  (one LOP3)
+__device__ __forceinline__ uint32_t bsel(uint32_t mask, uint32_t a, uint32_t b) { return (a & mask) | (b & ~mask); }
+// a * b + c on the FMA pipe (IMAD), keeps shifts/adds off the ALU pipe
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
 
 // L2 eviction policies: the check-node state is re-read every iteration and must stay L2
 // resident (evict_last); the soft input streams through once (evict_first).
@@ -209,21 +218,24 @@ __device__ __forceinline__ int process_pair(int8_t* __restrict__ L, const uint2*
         }
     }
 
+    // candidates for -(old message): old >= 0 -> -min(m, 31), old < 0 -> +m; the argmin link takes m1
+    const uint32_t n0p = vsub(0u, vmin(m0, h2(31))), n1p = vsub(0u, vmin(m1, h2(31)));
+    const uint32_t nx01p = n0p ^ n1p;
     uint32_t k0 = h2(0x7fff), k1 = h2(0x7fff), sx = 0;
 #pragma unroll
     for (int d = 0; d < DEG_MAX; ++d) {
         const bool live = UNIFORM || (d < 2) || (d - 2 < lv.cnt);
         if (live) {
             const uint32_t raw = *reinterpret_cast<const uint16_t*>(L + adr[d]);
-            const uint32_t l = prmt(raw, 0, sel[d] & 0xffffu);
+            const uint32_t l = prmt(raw, 0, sel[d]); // PRMT reads selector bits 15:0 only
             // stored message: +-(d == argmin ? min1 : min0), clamped to [-32, 31]
             const uint32_t hot = (!WIDE || d < 16) ? hot_lo : hot_hi;
             const uint32_t nsg = (!WIDE || d < 16) ? nsg_lo : nsg_hi;
             const uint32_t im = signmask(hot << (15 - (d & 15)));
             const uint32_t nm = signmask(nsg << (15 - (d & 15))); // 0xFFFF where the old message was >= 0
-            const uint32_t mc = m0 ^ (x01 & im);
-            const uint32_t negold = vmax(vsub(mc ^ nm, nm), h2(-31)); // -(old message)
-            uint32_t x = vmin(vmax(vadd(l, negold), h2(-128)), h2(127)); // vqsub
+            const uint32_t xa = vadd(l, n0p ^ (nx01p & im));      // l - old, old >= 0
+            const uint32_t xb = vadd(l, m0 ^ (x01 & im));         // l - old, old < 0
+            uint32_t x = vmin(vmax(bsel(nm, xa, xb), h2(-128)), h2(127)); // vqsub
             if (d == 1 && first)
                 x &= 0xffff0000u; // node A (check 0) has no such link: neutral value
             v[d] = x;
@@ -231,7 +243,7 @@ __device__ __forceinline__ int process_pair(int8_t* __restrict__ L, const uint2*
             // |x| saturated to 127, minus beta = 1, floored at 0:  max(x - 1, ~x, 0), capped at 126
             const uint32_t mg = vmin(vmax(vmax(vadd(x, h2(-1)), ~x), 0u), h2(126));
             mag[d] = mg;
-            uint32_t key = mg * 32u + h2(d);
+            uint32_t key = imad(mg, 32u, h2(d));
             if (d == 1 && first)
                 key |= 0x00007fffu; // never the minimum
             k1 = vmin(k1, vmax(k0, key));
@@ -243,17 +255,25 @@ __device__ __forceinline__ int process_pair(int8_t* __restrict__ L, const uint2*
     }
     const uint32_t min0 = (k0 >> 5) & 0x07ff07ffu;
     const uint32_t min1 = (k1 >> 5) & 0x07ff07ffu;
+    // new posterior = v +- m, m = min over the OTHER links = min0 + min1 - min(mag, min1):
+    //   v + m = (v + s01 + 1) + ~t,   v - m = (v - s01) + t,   t = min(mag, min1)
     const uint32_t s01 = vadd(min0, min1);
+    const uint32_t s01p1 = vadd(s01, h2(1)), ns01 = vsub(0u, s01);
     uint32_t newsg_lo = 0, newsg_hi = 0, syn = 0, zer = 0;
 #pragma unroll
-    for (int d = 0; d < DEG_MAX; ++d) {
+    for (int dd = 0; dd < DEG_MAX; ++dd) {
+        const int d = DEG_MAX - 1 - dd; // descending: the sign bits are shifted in from the top
         const bool live = UNIFORM || (d < 2) || (d - 2 < lv.cnt);
+        if (!WIDE || d < 16)
+            newsg_lo = vadd(newsg_lo, newsg_lo);
+        else
+            newsg_hi = vadd(newsg_hi, newsg_hi);
         if (live) {
-            // magnitude = min over the OTHER links = min0 + min1 - min(mag, min1)
-            const uint32_t m = vsub(s01, vmin(mag[d], min1));
+            const uint32_t t = vmin(mag[d], min1);
+            const uint32_t np = vadd(vadd(v[d], s01p1), ~t);
+            const uint32_t nn = vadd(vadd(v[d], ns01), t);
             const uint32_t ng = signmask(sx ^ v[d]); // product of the other signs, zero counts as +
-            const uint32_t out = vsub(m ^ ng, ng);
-            const uint32_t nl = vmin(vmax(vadd(v[d], out), h2(-128)), h2(127)); // vqadd
+            const uint32_t nl = vmin(vmax(bsel(ng, nn, np), h2(-128)), h2(127)); // vqadd
             const uint32_t packed = prmt(nl, 0, sel[d] >> 16);
             if (d == 1 && first)
                 L[adr[d]] = (int8_t)(nl >> 16); // only node B's link exists (low byte of that word)
@@ -261,9 +281,9 @@ __device__ __forceinline__ int process_pair(int8_t* __restrict__ L, const uint2*
                 *reinterpret_cast<uint16_t*>(L + adr[d]) = (uint16_t)packed;
             const uint32_t bit = ng & 0x00010001u;
             if (!WIDE || d < 16)
-                newsg_lo |= bit << (d & 15);
+                newsg_lo = vadd(newsg_lo, bit);
             else
-                newsg_hi |= bit << (d & 15);
+                newsg_hi = vadd(newsg_hi, bit);
             if (SELF_CHECK) {
                 uint32_t nlc = nl;
                 if (d == 1 && first)
