@@ -81,7 +81,7 @@ struct dvbs2b200_code {
     int ldpc_ctas = 0; // resident LDPC CTAs per SM
     uint64_t launches = 0;
     // staging for the host-pointer entry points
-    DevBuf d_in, d_mid, d_out, d_post, d_i32a, d_i32b, d_n0, d_llr, d_sync, d_scratch, d_flag;
+    DevBuf d_in, d_mid, d_out, d_post, d_i32a, d_i32b, d_n0, d_llr, d_sync, d_scratch, d_flag, d_prof;
 };
 
 namespace {
@@ -239,9 +239,37 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
         CU(cudaMemsetAsync(h->d_sync.p, 0, words * sizeof(unsigned), stream));
         p.gsync = (unsigned*)h->d_sync.p;
     }
+#ifdef DVBS2_PHASE_PROFILE
+    const char* prof_path = getenv("DVBS2B200_PHASE_PROFILE"); // diagnostics build: per-CTA cycles per phase
+#else
+    const char* prof_path = nullptr;
+#endif
+    if (prof_path) {
+        int rc = h->d_prof.ensure((size_t)grid * 8 * sizeof(unsigned long long));
+        if (rc)
+            return rc;
+        p.prof = (unsigned long long*)h->d_prof.p;
+    }
     cudaError_t e = ldpc_launch(p, hd.max_cnt, hd.uniform_cnt != 0, grid, smem, stream);
     if (e != cudaSuccess)
         return cuda_fail(e, "ldpc_launch");
+    if (prof_path) {
+        std::vector<unsigned long long> host((size_t)grid * 8);
+        CU(cudaStreamSynchronize(stream));
+        CU(cudaMemcpy(host.data(), h->d_prof.p, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        if (FILE* f = fopen(prof_path, "w")) {
+            static const char* names[8] = { "load", "syndrome_pass", "pair_steps", "narrow_runs", "wide_steps", "iteration_end",
+                                            "output", "total" };
+            for (int k = 0; k < 8; ++k) {
+                double sum = 0;
+                for (int b = 0; b < grid; ++b)
+                    sum += (double)host[(size_t)b * 8 + k];
+                fprintf(f, "%s %.0f\n", names[k], sum / grid);
+            }
+            fprintf(f, "ctas %d frames %d\n", grid, frames);
+            fclose(f);
+        }
+    }
     h->launches += 1;
     return DVBS2B200_OK;
 }
@@ -472,7 +500,7 @@ void dvbs2b200_code_destroy(dvbs2b200_code* h)
     DeviceGuard g(h->device);
     if (h->stream)
         cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : { &h->d_in, &h->d_mid, &h->d_out, &h->d_post, &h->d_i32a, &h->d_i32b, &h->d_n0, &h->d_llr, &h->d_sync, &h->d_scratch, &h->d_flag })
+    for (DevBuf* b : { &h->d_in, &h->d_mid, &h->d_out, &h->d_post, &h->d_i32a, &h->d_i32b, &h->d_n0, &h->d_llr, &h->d_sync, &h->d_scratch, &h->d_flag, &h->d_prof })
         b->release();
     if (h->d_blob)
         cudaFree(h->d_blob);

@@ -2,6 +2,7 @@
 #include "code_tables.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace dvbs2b200 {
@@ -116,18 +117,29 @@ void build_schedule(const LdpcTableDef& def, Schedule& s)
     // class of a wavefront step: 0 wide (all warps), 1 narrow scalar on warp 0, 2 link parallel.
     // Instruction cost model (measured on B200): a scalar check-node update is ~55 warp instructions
     // per link for up to 32 nodes, a link-parallel pass ~150 per warp of (node, link) lanes.
+    // tuning knobs (diagnostics): DVBS2B200_LP_LANES = link-parallel up to that many (node, link) lanes
+    // per level instead of the cost model; DVBS2B200_W0_MAX = largest level run on warp 0 alone
+    const char* env_lp = getenv("DVBS2B200_LP_LANES");
+    const char* env_w0 = getenv("DVBS2B200_W0_MAX");
+    const int lp_lanes = env_lp ? atoi(env_lp) : -1;
+    const int w0_max = env_w0 ? atoi(env_w0) : 32;
     auto step_class = [&](const StepRec& st) {
-        if (st.count == 0 || st.count > 32)
+        if (st.count == 0)
             return 0;
         const int G = group_lanes(st.layer), deg = (int)per_layer[st.layer].size() + 2;
         const int lp_warps = ((int)st.count * G + 31) / 32;
-        if (lp_warps <= 6 && 150 * lp_warps < 55 * deg)
-            return 2;
-        // high-degree codes (> 16 links): a scalar level is a ~1600-instruction dependent chain on one
-        // warp; spreading it over the links pays up to 14 nodes per level even with several passes
-        if (G == 32 && st.count <= 14)
-            return 2;
-        return 1;
+        if (lp_lanes >= 0) {
+            if ((int)st.count * G <= lp_lanes)
+                return 2;
+        } else if (st.count <= 32) {
+            if (lp_warps <= 6 && 150 * lp_warps < 55 * deg)
+                return 2;
+            // high-degree codes (> 16 links): a scalar level is a ~1600-instruction dependent chain on one
+            // warp; spreading it over the links pays up to 14 nodes per level even with several passes
+            if (G == 32 && st.count <= 14)
+                return 2;
+        }
+        return (int)st.count <= w0_max ? 1 : 0;
     };
     // runs of consecutive narrow steps of one layer and one class
     for (size_t k = 0; k < s.steps.size();) {

@@ -31,6 +31,9 @@ struct LdpcLaunch {
     int out_bytes;
     int8_t* llr_post;     // [frames][N] or null, 4-byte aligned
     int32_t* trials_left; // [frames] or null
+    // optional per-CTA cycle counters [grid][8]: load, syndrome pass, pair steps, runs, wide steps,
+    // iteration-end barrier, output, total (diagnostics: DVBS2B200_PHASE_PROFILE)
+    unsigned long long* prof;
 };
 
 // fills the smem_* offsets of p (if non-null) and returns the dynamic shared memory size

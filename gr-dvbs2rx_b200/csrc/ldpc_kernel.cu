@@ -462,12 +462,15 @@ __device__ __noinline__ int lp_run(int8_t* __restrict__ L, const uint2* __restri
         const bool self_check = (s0 + k == last_step);
         load_state(j_nxt, w_nxt, sg_nxt);
         const int j_nn = load_j(k + 2);
-        for (int item = tid; (item >> gshift) < count; item += nthreads) {
-            int j;
-            uint32_t w, sg;
-            if (item == tid) {
-                j = j_cur, w = w_cur, sg = sg_cur;
-            } else {
+        // every lane of the participating warps runs every pass (warp-wide shuffles / ballots below)
+        for (int item0 = 0; item0 < (count << gshift); item0 += nthreads) {
+            const int item = item0 + tid;
+            const bool grp = (item >> gshift) < count;
+            int j = 0;
+            uint32_t w = 0, sg = 0;
+            if (item0 == 0) {
+                j = j_cur < 0 ? 0 : j_cur, w = w_cur, sg = sg_cur;
+            } else if (grp) {
                 j = (int)work[work_off + (item >> gshift)];
                 load_state(j, w, sg);
             }
@@ -489,6 +492,7 @@ __device__ __noinline__ int lp_run(int8_t* __restrict__ L, const uint2* __restri
                 sidx += (sidx < 0) ? 360 : 0;
                 adr = data_link ? data_addr(gbase, sidx) : 0;
             }
+            live = live && grp;
             int x = 0, key = 0x7fffffff;
             if (live) {
                 const int l = (int)L[adr];
@@ -497,17 +501,37 @@ __device__ __noinline__ int lp_run(int8_t* __restrict__ L, const uint2* __restri
                 x = min(max(l - old, -128), 127);
                 key = max(min(abs(x), 127) - 1, 0) * 32 + link;
             }
-            const int k0 = __reduce_min_sync(gmask, key);
-            const int k1 = __reduce_min_sync(gmask, key == k0 ? 0x7fffffff : key);
-            const unsigned sx = __reduce_xor_sync(gmask, (unsigned)x);
+            // Two smallest keys and the sign parity over the G lanes of the check node.  REDUX with a
+            // member mask that differs between the groups of a warp falls into a slow divergent path,
+            // so only full-warp groups use it; smaller groups use xor-butterfly shuffles and a ballot.
+            int k0, k1;
+            bool par;
+            if (G == 32) {
+                k0 = __reduce_min_sync(0xffffffffu, key);
+                k1 = __reduce_min_sync(0xffffffffu, key == k0 ? 0x7fffffff : key);
+                par = (int)__reduce_xor_sync(0xffffffffu, (unsigned)x) < 0;
+            } else {
+                int a0 = key, a1 = 0x7fffffff;
+#pragma unroll
+                for (int m = 1; m < 16; m <<= 1) {
+                    if (m < G) {
+                        const int b0 = __shfl_xor_sync(0xffffffffu, a0, m), b1 = __shfl_xor_sync(0xffffffffu, a1, m);
+                        const int hi = max(a0, b0);
+                        a0 = min(a0, b0);
+                        a1 = min(hi, min(a1, b1));
+                    }
+                }
+                k0 = a0, k1 = a1;
+                par = __popc(__ballot_sync(0xffffffffu, x < 0) & gmask) & 1;
+            }
             const int min0 = k0 >> 5, min1 = k1 >> 5, arg = k0 & 31;
             const int m = (link == arg) ? min1 : min0;
-            const bool neg = (int)(sx ^ (unsigned)x) < 0;
+            const bool neg = par != (x < 0);
             const int nl = min(max(x + (neg ? -m : m), -128), 127);
             if (live)
                 L[adr] = (int8_t)nl;
-            const unsigned signs = __ballot_sync(gmask, live && neg) >> (lane & ~(G - 1));
-            if (link == 0) {
+            const unsigned signs = (__ballot_sync(0xffffffffu, live && neg) & gmask) >> (lane & ~(G - 1));
+            if (link == 0 && grp) {
                 const uint32_t lo = (uint32_t)min(min0, 32) | ((uint32_t)min(min1, 32) << 6) | ((uint32_t)arg << 12);
                 if (!WIDE) {
                     stg_hint(mp + hsel, lo | (signs << 17), pol);
@@ -517,9 +541,9 @@ __device__ __noinline__ int lp_run(int8_t* __restrict__ L, const uint2* __restri
                 }
             }
             if (self_check) {
-                const unsigned syn = __reduce_xor_sync(gmask, live ? (unsigned)nl : 0u);
-                const unsigned zero = __ballot_sync(gmask, live && nl == 0);
-                self_bad |= ((int)syn < 0) | (zero != 0);
+                const unsigned negs = __ballot_sync(0xffffffffu, live && nl < 0) & gmask;
+                const unsigned zero = __ballot_sync(0xffffffffu, live && nl == 0) & gmask;
+                self_bad |= (int)((__popc(negs) & 1) | (zero != 0)) & (int)grp;
             }
         }
         sub_barrier(nwarps); // this level's writes are visible to the next level's lanes
@@ -638,6 +662,21 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
     }
     mbar_wait(bar, 0);
 
+#ifdef DVBS2_PHASE_PROFILE
+    // diagnostics build: cycles per phase, per CTA (load, syndrome pass, pair steps, narrow runs, wide steps,
+    // iteration end, output, total) -> p.prof[blockIdx][8]
+    unsigned long long t_phase[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    const long long t_kernel = clock64();
+    long long t_mark = t_kernel;
+#define LAP(slot)                                                   \
+    do {                                                            \
+        const long long now__ = clock64();                          \
+        t_phase[slot] += (unsigned long long)(now__ - t_mark);      \
+        t_mark = now__;                                             \
+    } while (0)
+#else
+#define LAP(slot) ((void)0)
+#endif
     for (int f = blockIdx.x; f < p.frames; f += gridDim.x) {
         // ---- streaming input: wait until the host->device copy of this frame's chunk has landed ----
         if (p.ready) {
@@ -671,6 +710,7 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
             }
         }
         __syncthreads();
+        LAP(0);
 
         // ---- while (bad() && --trials >= 0) update();  layered_decoder.hh:153 ----------------------
         int trials = p.max_trials;
@@ -687,6 +727,7 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
                     }
                 }
                 bad = __syncthreads_or((int)flag);
+                LAP(1);
             } else {
                 bad = 1;
             }
@@ -778,9 +819,11 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
                             process_cn<CNT_MAX, UNIFORM, WIDE, false>(L, edges, lv, layer, j, K, q, mp, zero_state, pol_keep, false, 0, 0);
                     }
                 }
+                LAP(count == 0 ? 2 : (is_run ? 3 : 4));
                 s = next;
             }
             proven_bad = __syncthreads_or(self_bad);
+            LAP(5);
         }
 
         // ---- outputs -----------------------------------------------------------------------------------
@@ -827,7 +870,15 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
             }
         }
         __syncthreads(); // L is reused by the next frame
+        LAP(6);
     }
+#ifdef DVBS2_PHASE_PROFILE
+    if (p.prof && tid == 0) {
+        t_phase[7] = (unsigned long long)(clock64() - t_kernel);
+        for (int k = 0; k < 8; ++k)
+            p.prof[(size_t)blockIdx.x * 8 + k] = t_phase[k];
+    }
+#endif
 }
 
 template <int CNT_MAX, bool UNIFORM, bool WIDE>
