@@ -78,7 +78,8 @@ struct dvbs2b200_code {
     BlobHeader hdr;
     uint8_t* d_blob = nullptr;
     size_t ldpc_smem = 0;
-    int ldpc_ctas = 0; // resident LDPC CTAs per SM
+    int ldpc_ctas = 0;      // resident LDPC CTAs per SM
+    int ldpc_ctas_tmem = 0; // same for the kernel variant that keeps wavefront state in tensor memory
     uint64_t launches = 0;
     // staging for the host-pointer entry points
     DevBuf d_in, d_mid, d_out, d_post, d_i32a, d_i32b, d_n0, d_llr, d_sync, d_scratch, d_flag, d_prof;
@@ -137,11 +138,18 @@ int create_from_blob(dvbs2b200_code** out, int device, std::vector<uint8_t>&& bl
         return bail(cuda_fail(e, "cudaMemcpy(tables)"));
     h->ldpc_smem = ldpc_smem_bytes(h->hdr.N, h->hdr.smem_bytes, nullptr);
     if (h->hdr.max_cnt <= 28 && h->ldpc_smem <= (size_t)h->smem_optin)
-        h->ldpc_ctas = ldpc_ctas_per_sm(h->hdr.max_cnt, h->hdr.uniform_cnt != 0, h->ldpc_smem);
+        h->ldpc_ctas = ldpc_ctas_per_sm(h->hdr.max_cnt, h->hdr.uniform_cnt != 0, false, h->ldpc_smem);
+    if (h->ldpc_ctas > 0 && h->hdr.tmem_cols > 0)
+        h->ldpc_ctas_tmem = ldpc_ctas_per_sm(h->hdr.max_cnt, h->hdr.uniform_cnt != 0, true, h->ldpc_smem);
+    if (getenv("DVBS2B200_DEBUG"))
+        fprintf(stderr, "[dvbs2b200] table %d: ldpc smem %zu B, %d CTAs/SM (%d with TMEM state, %d columns)\n", h->hdr.table,
+                h->ldpc_smem, h->ldpc_ctas, h->ldpc_ctas_tmem, h->hdr.tmem_cols);
     if (const char* cap = getenv("DVBS2B200_LDPC_CTAS_PER_SM")) { // tuning knob: cap the resident CTAs per SM
         int c = atoi(cap);
         if (c > 0 && c < h->ldpc_ctas)
             h->ldpc_ctas = c;
+        if (c > 0 && c < h->ldpc_ctas_tmem)
+            h->ldpc_ctas_tmem = c;
     }
     *out = h;
     return DVBS2B200_OK;
@@ -167,9 +175,9 @@ struct DeviceGuard {
 int ldpc_out_bytes(const BlobHeader& h, int output_mode) { return (output_mode ? h.kldpc_out : h.N) / 8; }
 
 // grid size: persistent CTAs, as many as are resident at once; in group mode a multiple of the group
-int ldpc_grid(const dvbs2b200_code* h, int frames, int group)
+int ldpc_grid(const dvbs2b200_code* h, int frames, int group, bool tmem)
 {
-    const int resident = h->sm_count * h->ldpc_ctas;
+    const int resident = h->sm_count * (tmem ? h->ldpc_ctas_tmem : h->ldpc_ctas);
     int grid = std::min(frames, resident);
     if (group > 1)
         grid = std::min(frames, (resident / group) * group);
@@ -214,7 +222,10 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
     p.work = reinterpret_cast<const uint16_t*>(h->d_blob + hd.order_off);
     size_t smem = ldpc_smem_bytes(hd.N, hd.smem_bytes, &p);
     const int group = term_group > 1 ? term_group : 0;
-    const int grid = ldpc_grid(h, frames, group);
+    // wavefront state in tensor memory: per-frame mode only (the cooperative launch of the group mode is
+    // sized by the occupancy calculator, which does not co-schedule kernels that use TMEM)
+    const bool tmem = group == 0 && h->ldpc_ctas_tmem >= h->ldpc_ctas && h->ldpc_ctas_tmem > 0 && !getenv("DVBS2B200_NO_TMEM");
+    const int grid = ldpc_grid(h, frames, group, tmem);
     {
         int rc = h->d_scratch.ensure((size_t)grid * hd.R * hd.msg_words * sizeof(uint32_t));
         if (rc)
@@ -250,7 +261,7 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
             return rc;
         p.prof = (unsigned long long*)h->d_prof.p;
     }
-    cudaError_t e = ldpc_launch(p, hd.max_cnt, hd.uniform_cnt != 0, grid, smem, stream);
+    cudaError_t e = ldpc_launch(p, hd.max_cnt, hd.uniform_cnt != 0, tmem, grid, smem, stream);
     if (e != cudaSuccess)
         return cuda_fail(e, "ldpc_launch");
     if (prof_path) {

@@ -37,7 +37,7 @@ const ModcodDef* find_modcod(int standard, int framesize, int rate)
 // such layers we compute level[j] = 1 + max(level[j'] : j' < j touches one of j's bits); check
 // nodes of equal level are independent, and running the levels in order reproduces the serial
 // result bit for bit.
-void build_schedule(const LdpcTableDef& def, Schedule& s)
+void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem)
 {
     const int q = def.q;
     s = Schedule();
@@ -189,6 +189,37 @@ void build_schedule(const LdpcTableDef& def, Schedule& s)
         for (int g : groups)
             (sub ? dirty_sub : dirty_all)[g] = 1;
     }
+
+    // ---- tensor-memory columns for the state of wavefront steps (code_tables.h) --------------------
+    s.tcol.assign(s.steps.size(), kNoTmem);
+    if (use_tmem && s.max_cnt <= 13) { // one-word state only
+        int next_col = 0;
+        auto cols_needed = [&](const StepRec& st) {
+            if (st.count == 0 || (st.work_off & kStepLinkParallel))
+                return 0;
+            if (st.work_off & kStepRun)
+                return 1;                          // warp 0, one pass
+            return 2 * (((int)st.count + 191) / 192); // warps 0-3 and 4-5, per pass
+        };
+        // narrow runs first (they are the deepest chains); a run is placed whole or not at all
+        for (size_t k = 0; k < s.steps.size(); ++k) {
+            const StepRec& st = s.steps[k];
+            if (!(st.work_off & kStepRun) || (st.work_off & kStepLinkParallel) || st.run_len == 0)
+                continue;
+            if (next_col + (int)st.run_len > kTmemCols)
+                continue;
+            for (int t = 0; t < (int)st.run_len; ++t)
+                s.tcol[k + t] = (uint8_t)next_col++;
+        }
+        for (size_t k = 0; k < s.steps.size(); ++k) {
+            const StepRec& st = s.steps[k];
+            const int need = cols_needed(st);
+            if (need == 0 || (st.work_off & kStepRun) || next_col + need > kTmemCols)
+                continue;
+            s.tcol[k] = (uint8_t)next_col;
+            next_col += need;
+        }
+    }
 }
 
 // ---- GF(2^m) ---------------------------------------------------------------------------------
@@ -328,8 +359,25 @@ bool build_blob(int standard, int framesize, int rate, std::vector<uint8_t>& blo
     off += sizeof(EdgeRec) * s.edges.size();
     h.step_off = (uint32_t)off;
     off += sizeof(StepRec) * s.steps.size();
+    const size_t tcol_off = off;
+    off += s.tcol.size();
     off = align16(off);
     h.smem_bytes = (uint32_t)(off - h.smem_off);
+    // Use the tensor-memory kernel variant only when most of the scalar wavefront steps got columns:
+    // measured on B200, codes where under ~3/4 of them fit (DVB-S2 3/4, 3/5 normal) ran slower with a
+    // partial placement than with all state in L2, codes where they fit (1/2 normal, 2/3 short) faster.
+    h.tmem_cols = 0;
+    {
+        int placed = 0, scalar_steps = 0;
+        for (size_t k = 0; k < s.steps.size(); ++k) {
+            if (s.steps[k].count == 0 || (s.steps[k].work_off & kStepLinkParallel))
+                continue;
+            ++scalar_steps;
+            placed += s.tcol[k] != kNoTmem;
+        }
+        if (placed > 0 && 4 * placed >= 3 * scalar_steps)
+            h.tmem_cols = kTmemCols;
+    }
     h.order_off = (uint32_t)off;
     off = align16(off + sizeof(uint16_t) * s.order.size());
     std::vector<uint16_t> al, lg;
@@ -346,6 +394,7 @@ bool build_blob(int standard, int framesize, int rate, std::vector<uint8_t>& blo
     memcpy(blob.data() + h.edge_off, s.edges.data(), sizeof(EdgeRec) * s.edges.size());
     if (!s.steps.empty())
         memcpy(blob.data() + h.step_off, s.steps.data(), sizeof(StepRec) * s.steps.size());
+    memcpy(blob.data() + tcol_off, s.tcol.data(), s.tcol.size());
     if (!s.order.empty())
         memcpy(blob.data() + h.order_off, s.order.data(), sizeof(uint16_t) * s.order.size());
     memcpy(blob.data() + h.antilog_off, al.data(), sizeof(uint16_t) * al.size());

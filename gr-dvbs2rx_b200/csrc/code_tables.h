@@ -29,7 +29,7 @@ const ModcodDef* find_modcod(int standard, int framesize, int rate);
 
 // ---- packed blob ---------------------------------------------------------------------------
 constexpr uint32_t kBlobMagic = 0x32425344u; // "DSB2"
-constexpr uint32_t kBlobVersion = 8;
+constexpr uint32_t kBlobVersion = 9;
 
 // One per layer, 8 bytes, lives in shared memory.
 struct LayerRec {
@@ -68,6 +68,14 @@ constexpr uint32_t kStepWarpsShift = 26;         // 3 bits: warps taking part in
 constexpr uint32_t kStepLinkParallel = 1u << 29; // run class: link parallel (else one node per lane)
 constexpr uint32_t kStepOffMask = (1u << 24) - 1;
 
+// Tensor memory as scratch for the check-node state of order-sensitive layers.  Those layers are a
+// dependent chain of short steps, and the ~700-cycle L2 round trip for the state word sits on that
+// chain; TMEM (256 KB per SM, otherwise idle here) answers in ~30 cycles.  Each CTA owns kTmemCols
+// columns (3 CTAs x 128 of the SM's 512); a step gets one column per 4 warps and pass, the host
+// assigns them (narrow runs first) until the budget is spent -- the rest stays in L2.
+constexpr int kTmemCols = 128;
+constexpr uint8_t kNoTmem = 0xff;
+
 struct BlobHeader {
     uint32_t magic, version, total_bytes, reserved0;
     int32_t table, standard, framesize, rate;
@@ -79,9 +87,9 @@ struct BlobHeader {
     int32_t n_steps_total, n_conflict_layers;
     int32_t steps_per_iter, max_depth;
     int32_t uniform_cnt; // 1 if every layer has max_cnt data links per check node
-    int32_t reserved2;
+    int32_t tmem_cols;   // TMEM columns a CTA allocates (0 or kTmemCols)
     // section offsets from the start of the blob, all 16-byte aligned
-    uint32_t smem_off, smem_bytes; // [LayerRec q][EdgeRec n_circ][StepRec steps_per_iter]: TMA-staged
+    uint32_t smem_off, smem_bytes; // [LayerRec q][EdgeRec n_circ][StepRec steps][uint8 tmem column steps]: TMA-staged
     uint32_t layer_off, edge_off;  // (inside the smem section)
     uint32_t step_off, order_off;  // StepRec[] (inside the smem section), uint16 work[] (global)
     uint32_t antilog_off, log_off; // uint16[2^m] each: alpha^i (i < 2^m-1), log(x)
@@ -118,9 +126,10 @@ struct Schedule {
     std::vector<EdgeRec> edges;
     std::vector<StepRec> steps; // one iteration, in execution order
     std::vector<uint16_t> order; // work[]: check-node indices of the conflict steps
+    std::vector<uint8_t> tcol;   // per step: first TMEM column of its state, or kNoTmem
     int max_cnt = 0, min_cnt = 1 << 30, steps_per_iter = 0, max_depth = 0, conflict_layers = 0, barriers_per_iter = 0;
 };
-void build_schedule(const LdpcTableDef& def, Schedule& s);
+void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem = true);
 
 // ---- GF(2^m) / BCH host helpers --------------------------------------------------------------
 uint32_t bch_prim_poly(int framesize); // lib/bch_decoder_bb_impl.cc:58-63

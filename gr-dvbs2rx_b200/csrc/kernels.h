@@ -38,9 +38,9 @@ struct LdpcLaunch {
 
 // fills the smem_* offsets of p (if non-null) and returns the dynamic shared memory size
 size_t ldpc_smem_bytes(int N, uint32_t tab_bytes, LdpcLaunch* p);
-cudaError_t ldpc_launch(const LdpcLaunch& p, int max_cnt, bool uniform, int grid, size_t smem, cudaStream_t stream);
+cudaError_t ldpc_launch(const LdpcLaunch& p, int max_cnt, bool uniform, bool tmem, int grid, size_t smem, cudaStream_t stream);
 // resident CTAs per SM for this code's kernel instantiation (occupancy query)
-int ldpc_ctas_per_sm(int max_cnt, bool uniform, size_t smem);
+int ldpc_ctas_per_sm(int max_cnt, bool uniform, bool tmem, size_t smem);
 // true when the check-node state takes two words per node (more than 13 data links)
 bool ldpc_wide_state(int max_cnt);
 

@@ -30,6 +30,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace dvbs2b200 {
@@ -37,6 +39,7 @@ namespace dvbs2b200 {
 namespace {
 
 constexpr int kPairs = 180; // check-node pairs per layer
+constexpr int kTmemColsDev = 128; // = code_tables.h kTmemCols
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -144,6 +147,22 @@ __device__ __forceinline__ void stg_hint(uint4* p, uint4 v, uint64_t pol)
     asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
                  "r"(v.w), "l"(pol)
                  : "memory");
+}
+
+// Tensor memory used as plain scratch (SASS: LDTM / STTM): one 32-bit cell per lane and column; a
+// warp reaches the 32 TMEM lanes of its quarter (warp id % 4).  ~30 cycles for a load + store pair
+// against ~700 for the L2 round trip (tools/ubench/tmem_test.cu).
+__device__ __forceinline__ uint32_t tmem_ld(uint32_t taddr)
+{
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    return r;
+}
+__device__ __forceinline__ void tmem_st(uint32_t taddr, uint32_t v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 struct LayerView {
@@ -315,7 +334,7 @@ __device__ __forceinline__ int process_pair(int8_t* __restrict__ L, const uint2*
 template <int CNT_MAX, bool UNIFORM, bool WIDE, bool SELF_CHECK>
 __device__ __forceinline__ int process_cn(int8_t* __restrict__ L, const uint2* __restrict__ edges, const LayerView& lv, int layer,
                                           int j, int K, int q, uint32_t* __restrict__ msg_pair, bool zero_state, uint64_t pol,
-                                          bool have_state, uint32_t pw, uint32_t psg)
+                                          bool have_state, uint32_t pw, uint32_t psg, uint32_t* state_out = nullptr)
 {
     constexpr int DEG_MAX = CNT_MAX + 2;
     const int hsel = j >= kPairs; // which node of the pair
@@ -387,7 +406,9 @@ __device__ __forceinline__ int process_cn(int8_t* __restrict__ L, const uint2* _
         }
     }
     const uint32_t lo = (uint32_t)min(min0, 32) | ((uint32_t)min(min1, 32) << 6) | ((uint32_t)arg << 12);
-    if (!WIDE) {
+    if (state_out) {
+        *state_out = lo | (new_signs << 17); // one-word state kept in tensor memory by the caller
+    } else if (!WIDE) {
         stg_hint(msg_pair + hsel, lo | (new_signs << 17), pol);
     } else {
         stg_hint(msg_pair + hsel, lo, pol);
@@ -554,13 +575,41 @@ __device__ __noinline__ int lp_run(int8_t* __restrict__ L, const uint2* __restri
 }
 
 // ---- run of narrow wavefront levels on warp 0, one check node per lane, ordered by __syncwarp() -------
-template <int CNT_MAX, bool UNIFORM, bool WIDE>
+template <int CNT_MAX, bool UNIFORM, bool WIDE, bool TMEM>
 __device__ __noinline__ int scalar_run(int8_t* __restrict__ L, const uint2* __restrict__ edges, const uint2* __restrict__ steps,
                                        const uint16_t* __restrict__ work, uint32_t* __restrict__ msg, const LayerView lv, int layer,
-                                       int s0, int run_len, int last_step, int K, int q, bool zero_state, uint64_t pol, int tid)
+                                       int s0, int run_len, int last_step, int K, int q, bool zero_state, uint64_t pol, int tid,
+                                       const uint8_t* __restrict__ tcol, uint32_t tmem_base)
 {
     constexpr int MW = WIDE ? 2 : 1;
     int self_bad = 0;
+    if (TMEM && tcol[s0] != 0xff) {
+        // state of this run lives in tensor memory: one column per level, lane = position in the level
+        int j_cur = -1, j_nxt = -1;
+        {
+            const uint2 st = steps[s0];
+            j_cur = (tid < (int)(st.x >> 16)) ? (int)work[(st.y & 0x00ffffffu) + tid] : -1;
+        }
+        for (int k = 0; k < run_len; ++k) {
+            if (k + 1 < run_len) {
+                const uint2 st = steps[s0 + k + 1];
+                j_nxt = (tid < (int)(st.x >> 16)) ? (int)work[(st.y & 0x00ffffffu) + tid] : -1;
+            }
+            const uint32_t taddr = tmem_base + (uint32_t)tcol[s0 + k];
+            uint32_t w = zero_state ? 0u : tmem_ld(taddr);
+            if (j_cur >= 0) {
+                if (s0 + k == last_step)
+                    self_bad |= process_cn<CNT_MAX, UNIFORM, WIDE, true>(L, edges, lv, layer, j_cur, K, q, msg, zero_state, pol, true, w, w >> 17, &w);
+                else
+                    process_cn<CNT_MAX, UNIFORM, WIDE, false>(L, edges, lv, layer, j_cur, K, q, msg, zero_state, pol, true, w, w >> 17, &w);
+            }
+            tmem_st(taddr, w);
+            __syncwarp();
+            j_cur = j_nxt;
+            j_nxt = -1;
+        }
+        return self_bad;
+    }
     // this lane's check node and its state word are fetched one level ahead
     auto load_j = [&](int k) -> int {
         if (k >= run_len)
@@ -631,7 +680,7 @@ __device__ __forceinline__ uint32_t check_pair(const int8_t* __restrict__ L, con
     return (s | z) & 0x8080u;
 }
 
-template <int CNT_MAX, bool UNIFORM, bool WIDE>
+template <int CNT_MAX, bool UNIFORM, bool WIDE, bool TMEM>
 __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kernel(const LdpcLaunch p)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -639,8 +688,10 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
     const uint2* layers = reinterpret_cast<const uint2*>(smem + p.smem_tab_off);
     const uint2* edges = reinterpret_cast<const uint2*>(smem + p.smem_tab_off + (size_t)p.q * 8);
     const uint2* steps = reinterpret_cast<const uint2*>(smem + p.smem_tab_off + (size_t)p.q * 8 + (size_t)p.n_circ * 8);
+    const uint8_t* tcol = smem + p.smem_tab_off + (size_t)p.q * 8 + (size_t)p.n_circ * 8 + (size_t)p.n_steps * 8;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + p.smem_bar_off);
     __shared__ int s_group_bad;
+    __shared__ uint32_t s_tmem_base;
 
     const int tid = threadIdx.x;
     const int N = p.N, K = p.K, q = p.q, R = p.R;
@@ -654,7 +705,19 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // tensor memory for the state of the order-sensitive layers: warp 0 allocates (and frees at the end)
+    if (TMEM && tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "n"(kTmemColsDev)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (TMEM)
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (TMEM)
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = TMEM ? s_tmem_base : 0u;
+    const uint32_t tmem_warp = tmem_base + ((uint32_t)((tid >> 5) & 3) << 21); // this warp's 32 TMEM lanes
     // stage the code tables once per CTA (TMA)
     if (tid == 0) {
         mbar_expect_tx(bar, p.tab_bytes);
@@ -804,19 +867,39 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
                             self_bad |= lp_run<WIDE>(L, edges, steps, work, msg, lv.cnt, lv.edge_begin, layer, s, run_len, sub_warps,
                                                      last_step, K, q, zero_state, pol_keep, tid);
                         else
-                            self_bad |= scalar_run<CNT_MAX, UNIFORM, WIDE>(L, edges, steps, work, msg, lv, layer, s, run_len, last_step,
-                                                                          K, q, zero_state, pol_keep, tid);
+                            self_bad |= scalar_run<CNT_MAX, UNIFORM, WIDE, TMEM>(L, edges, steps, work, msg, lv, layer, s, run_len, last_step,
+                                                                          K, q, zero_state, pol_keep, tid, tcol, tmem_base);
                     }
                 } else {
                     // wide wavefront level: single check nodes, one per thread
-                    for (int t = tid; t < count; t += kLdpcThreads) {
-                        const int j = (int)work[work_off + t];
-                        const int pp = j >= kPairs ? j - kPairs : j;
-                        uint32_t* mp = msg + ((size_t)layer * kPairs + pp) * 2 * MW;
-                        if (last)
-                            self_bad |= process_cn<CNT_MAX, UNIFORM, WIDE, true>(L, edges, lv, layer, j, K, q, mp, zero_state, pol_keep, false, 0, 0);
-                        else
-                            process_cn<CNT_MAX, UNIFORM, WIDE, false>(L, edges, lv, layer, j, K, q, mp, zero_state, pol_keep, false, 0, 0);
+                    const uint32_t tc = tcol[s];
+                    if (TMEM && tc != 0xffu) {
+                        // state in tensor memory: a column per 4 warps and pass, lane = thread
+                        for (int t0 = 0; t0 < count; t0 += kLdpcThreads) {
+                            const int t = t0 + tid;
+                            if (t0 + (tid & ~31) < count) { // warp-uniform: TMEM accesses are warp collectives
+                                const uint32_t taddr = tmem_warp + tc + 2u * (uint32_t)(t0 / kLdpcThreads) + (uint32_t)(tid >> 7);
+                                uint32_t w = zero_state ? 0u : tmem_ld(taddr);
+                                if (t < count) {
+                                    const int j = (int)work[work_off + t];
+                                    if (last)
+                                        self_bad |= process_cn<CNT_MAX, UNIFORM, WIDE, true>(L, edges, lv, layer, j, K, q, msg, zero_state, pol_keep, true, w, w >> 17, &w);
+                                    else
+                                        process_cn<CNT_MAX, UNIFORM, WIDE, false>(L, edges, lv, layer, j, K, q, msg, zero_state, pol_keep, true, w, w >> 17, &w);
+                                }
+                                tmem_st(taddr, w);
+                            }
+                        }
+                    } else {
+                        for (int t = tid; t < count; t += kLdpcThreads) {
+                            const int j = (int)work[work_off + t];
+                            const int pp = j >= kPairs ? j - kPairs : j;
+                            uint32_t* mp = msg + ((size_t)layer * kPairs + pp) * 2 * MW;
+                            if (last)
+                                self_bad |= process_cn<CNT_MAX, UNIFORM, WIDE, true>(L, edges, lv, layer, j, K, q, mp, zero_state, pol_keep, false, 0, 0);
+                            else
+                                process_cn<CNT_MAX, UNIFORM, WIDE, false>(L, edges, lv, layer, j, K, q, mp, zero_state, pol_keep, false, 0, 0);
+                        }
                     }
                 }
                 LAP(count == 0 ? 2 : (is_run ? 3 : 4));
@@ -872,6 +955,12 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
         __syncthreads(); // L is reused by the next frame
         LAP(6);
     }
+    if (TMEM) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid < 32)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemColsDev) : "memory");
+    }
 #ifdef DVBS2_PHASE_PROFILE
     if (p.prof && tid == 0) {
         t_phase[7] = (unsigned long long)(clock64() - t_kernel);
@@ -881,10 +970,10 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
 #endif
 }
 
-template <int CNT_MAX, bool UNIFORM, bool WIDE>
+template <int CNT_MAX, bool UNIFORM, bool WIDE, bool TMEM>
 cudaError_t launch_one(const LdpcLaunch& p, int grid, size_t smem, cudaStream_t stream)
 {
-    auto kern = ldpc_decode_kernel<CNT_MAX, UNIFORM, WIDE>;
+    auto kern = ldpc_decode_kernel<CNT_MAX, UNIFORM, WIDE, TMEM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess)
         return e;
@@ -896,16 +985,34 @@ cudaError_t launch_one(const LdpcLaunch& p, int grid, size_t smem, cudaStream_t 
     return cudaGetLastError();
 }
 
-template <int CNT_MAX, bool UNIFORM, bool WIDE>
+template <int CNT_MAX, bool UNIFORM, bool WIDE, bool TMEM>
 int occupancy_one(size_t smem)
 {
-    auto kern = ldpc_decode_kernel<CNT_MAX, UNIFORM, WIDE>;
+    auto kern = ldpc_decode_kernel<CNT_MAX, UNIFORM, WIDE, TMEM>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return 0;
-    int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kLdpcThreads, smem) != cudaSuccess)
+    if (!TMEM) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kLdpcThreads, smem) != cudaSuccess)
+            return 0;
+        return n;
+    }
+    // The occupancy calculator answers 1 for any kernel that contains tcgen05 instructions; the SM does
+    // co-schedule CTAs that each allocate a share of the 512 TMEM columns (measured: 3 CTAs x 128 columns
+    // run 1.6x faster than 1).  Compute the residency from the kernel's real resources instead.
+    cudaFuncAttributes fa;
+    int dev = 0, smem_sm = 0, regs_sm = 0, threads_sm = 0;
+    if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess || cudaGetDevice(&dev) != cudaSuccess)
         return 0;
-    return n;
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&threads_sm, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
+    const int regs_per_warp = ((fa.numRegs * 32 + 255) / 256) * 256;
+    const int by_regs = regs_sm / (regs_per_warp * (kLdpcThreads / 32));
+    const int by_smem = (int)((size_t)smem_sm / (smem + fa.sharedSizeBytes + 1024));
+    const int by_threads = threads_sm / kLdpcThreads;
+    const int by_tmem = 512 / kTmemColsDev;
+    return std::max(0, std::min(std::min(by_regs, by_smem), std::min(by_threads, by_tmem)));
 }
 
 } // namespace
@@ -941,42 +1048,42 @@ size_t ldpc_smem_bytes(int N, uint32_t tab_bytes, LdpcLaunch* p)
 // (every DVB-S2 normal-frame table) get the link count as a compile-time constant: no predication,
 // no dead link slots.  The rest take the predicated variant of the next size up.  The narrow state
 // word holds 15 sign bits (<= 13 data links), above that the wide (two-word) state is used.
-#define DVBS2_DISPATCH(CALL)                                              \
-    if (uniform) {                                                        \
-        switch (max_cnt) {                                                \
-        case 2: return CALL(2, true, false);                              \
-        case 3: return CALL(3, true, false);                              \
-        case 4: return CALL(4, true, false);                              \
-        case 5: return CALL(5, true, false);                              \
-        case 7: return CALL(7, true, false);                              \
-        case 8: return CALL(8, true, false);                              \
-        case 9: return CALL(9, true, false);                              \
-        case 11: return CALL(11, true, false);                            \
-        case 12: return CALL(12, true, false);                            \
-        case 16: return CALL(16, true, true);                             \
-        case 20: return CALL(20, true, true);                             \
-        case 25: return CALL(25, true, true);                             \
-        case 28: return CALL(28, true, true);                             \
-        default: break;                                                   \
-        }                                                                 \
-    }                                                                     \
-    if (max_cnt <= 5) return CALL(5, false, false);                       \
-    if (max_cnt <= 9) return CALL(9, false, false);                       \
-    if (max_cnt <= 13) return CALL(13, false, false);                     \
-    if (max_cnt <= 18) return CALL(18, false, true);                      \
-    if (max_cnt <= 28) return CALL(28, false, true);
+#define DVBS2_DISPATCH(CALL)                                                   \
+    if (uniform) {                                                             \
+        switch (max_cnt) {                                                     \
+        case 2: return tmem ? CALL(2, true, false, true) : CALL(2, true, false, false);   \
+        case 3: return tmem ? CALL(3, true, false, true) : CALL(3, true, false, false);   \
+        case 4: return tmem ? CALL(4, true, false, true) : CALL(4, true, false, false);   \
+        case 5: return tmem ? CALL(5, true, false, true) : CALL(5, true, false, false);   \
+        case 7: return tmem ? CALL(7, true, false, true) : CALL(7, true, false, false);   \
+        case 8: return tmem ? CALL(8, true, false, true) : CALL(8, true, false, false);   \
+        case 9: return tmem ? CALL(9, true, false, true) : CALL(9, true, false, false);   \
+        case 11: return tmem ? CALL(11, true, false, true) : CALL(11, true, false, false); \
+        case 12: return tmem ? CALL(12, true, false, true) : CALL(12, true, false, false); \
+        case 16: return CALL(16, true, true, false);                           \
+        case 20: return CALL(20, true, true, false);                           \
+        case 25: return CALL(25, true, true, false);                           \
+        case 28: return CALL(28, true, true, false);                           \
+        default: break;                                                        \
+        }                                                                      \
+    }                                                                          \
+    if (max_cnt <= 5) return tmem ? CALL(5, false, false, true) : CALL(5, false, false, false);    \
+    if (max_cnt <= 9) return tmem ? CALL(9, false, false, true) : CALL(9, false, false, false);    \
+    if (max_cnt <= 13) return tmem ? CALL(13, false, false, true) : CALL(13, false, false, false); \
+    if (max_cnt <= 18) return CALL(18, false, true, false);                    \
+    if (max_cnt <= 28) return CALL(28, false, true, false);
 
-cudaError_t ldpc_launch(const LdpcLaunch& p, int max_cnt, bool uniform, int grid, size_t smem, cudaStream_t stream)
+cudaError_t ldpc_launch(const LdpcLaunch& p, int max_cnt, bool uniform, bool tmem, int grid, size_t smem, cudaStream_t stream)
 {
-#define CALL(C, U, W) launch_one<C, U, W>(p, grid, smem, stream)
+#define CALL(C, U, W, T) launch_one<C, U, W, T>(p, grid, smem, stream)
     DVBS2_DISPATCH(CALL)
 #undef CALL
     return cudaErrorInvalidValue;
 }
 
-int ldpc_ctas_per_sm(int max_cnt, bool uniform, size_t smem)
+int ldpc_ctas_per_sm(int max_cnt, bool uniform, bool tmem, size_t smem)
 {
-#define CALL(C, U, W) occupancy_one<C, U, W>(smem)
+#define CALL(C, U, W, T) occupancy_one<C, U, W, T>(smem)
     DVBS2_DISPATCH(CALL)
 #undef CALL
     return 0;
