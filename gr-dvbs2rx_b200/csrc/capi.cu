@@ -137,13 +137,14 @@ int create_from_blob(dvbs2b200_code** out, int device, std::vector<uint8_t>&& bl
     if ((e = cudaMemcpy(h->d_blob, h->blob.data(), h->blob.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
         return bail(cuda_fail(e, "cudaMemcpy(tables)"));
     h->ldpc_smem = ldpc_smem_bytes(h->hdr.N, h->hdr.smem_bytes, nullptr);
+    auto ctas_per_sm = h->hdr.split_steps ? ldpc_ctas_per_sm_split : ldpc_ctas_per_sm_wavefront;
     if (h->hdr.max_cnt <= 28 && h->ldpc_smem <= (size_t)h->smem_optin)
-        h->ldpc_ctas = ldpc_ctas_per_sm(h->hdr.max_cnt, h->hdr.uniform_cnt != 0, false, h->ldpc_smem);
-    if (h->ldpc_ctas > 0 && h->hdr.tmem_cols > 0)
-        h->ldpc_ctas_tmem = ldpc_ctas_per_sm(h->hdr.max_cnt, h->hdr.uniform_cnt != 0, true, h->ldpc_smem);
+        h->ldpc_ctas = ctas_per_sm(h->hdr.max_cnt, h->hdr.uniform_cnt != 0, false, h->ldpc_smem);
+    if (h->ldpc_ctas > 0 && h->hdr.tmem_cols > 0 && !h->hdr.split_steps)
+        h->ldpc_ctas_tmem = ctas_per_sm(h->hdr.max_cnt, h->hdr.uniform_cnt != 0, true, h->ldpc_smem);
     if (getenv("DVBS2B200_DEBUG"))
-        fprintf(stderr, "[dvbs2b200] table %d: ldpc smem %zu B, %d CTAs/SM (%d with TMEM state, %d columns)\n", h->hdr.table,
-                h->ldpc_smem, h->ldpc_ctas, h->ldpc_ctas_tmem, h->hdr.tmem_cols);
+        fprintf(stderr, "[dvbs2b200] table %d: %s steps, ldpc smem %zu B, %d CTAs/SM (%d with TMEM state, %d columns)\n", h->hdr.table,
+                h->hdr.split_steps ? "split" : "wavefront", h->ldpc_smem, h->ldpc_ctas, h->ldpc_ctas_tmem, h->hdr.tmem_cols);
     if (const char* cap = getenv("DVBS2B200_LDPC_CTAS_PER_SM")) { // tuning knob: cap the resident CTAs per SM
         int c = atoi(cap);
         if (c > 0 && c < h->ldpc_ctas)
@@ -216,7 +217,7 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
     p.R = hd.R;
     p.q = hd.q;
     p.n_circ = hd.n_circ;
-    p.n_steps = hd.steps_per_iter;
+    p.n_steps = hd.n_steps_total;
     p.tab = h->d_blob + hd.smem_off;
     p.tab_bytes = hd.smem_bytes;
     p.work = reinterpret_cast<const uint16_t*>(h->d_blob + hd.order_off);
@@ -242,6 +243,10 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
     p.out_bytes = ldpc_out_bytes(hd, output_mode);
     p.llr_post = d_llr_post;
     p.trials_left = d_trials_left;
+    p.sm_count = h->sm_count;
+    p.stagger_ns = 0;
+    if (const char* sg = getenv("DVBS2B200_STAGGER_NS"))
+        p.stagger_ns = (unsigned int)atoi(sg);
     if (p.group) {
         size_t words = (size_t)(frames / p.group) * (max_trials + 2);
         int rc = h->d_sync.ensure(words * sizeof(unsigned));
@@ -256,25 +261,27 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
     const char* prof_path = nullptr;
 #endif
     if (prof_path) {
-        int rc = h->d_prof.ensure((size_t)grid * 8 * sizeof(unsigned long long));
+        int rc = h->d_prof.ensure((size_t)grid * 16 * sizeof(unsigned long long));
         if (rc)
             return rc;
         p.prof = (unsigned long long*)h->d_prof.p;
+        CU(cudaMemsetAsync(p.prof, 0, (size_t)grid * 16 * sizeof(unsigned long long), stream));
     }
-    cudaError_t e = ldpc_launch(p, hd.max_cnt, hd.uniform_cnt != 0, tmem, grid, smem, stream);
+    cudaError_t e = (hd.split_steps ? ldpc_launch_split : ldpc_launch_wavefront)(p, hd.max_cnt, hd.uniform_cnt != 0, tmem, grid, smem, stream);
     if (e != cudaSuccess)
         return cuda_fail(e, "ldpc_launch");
     if (prof_path) {
-        std::vector<unsigned long long> host((size_t)grid * 8);
+        std::vector<unsigned long long> host((size_t)grid * 16);
         CU(cudaStreamSynchronize(stream));
         CU(cudaMemcpy(host.data(), h->d_prof.p, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         if (FILE* f = fopen(prof_path, "w")) {
-            static const char* names[8] = { "load", "syndrome_pass", "pair_steps", "narrow_runs", "wide_steps", "iteration_end",
-                                            "output", "total" };
-            for (int k = 0; k < 8; ++k) {
+            static const char* names[13] = { "load", "syndrome_pass", "pair_steps", "narrow_runs", "wide_steps", "iteration_end",
+                                             "output", "total", "split_barrier_wait", "split_chain", "split_handover", "split_warp_levels",
+                                             "split_pre" };
+            for (int k = 0; k < 13; ++k) {
                 double sum = 0;
                 for (int b = 0; b < grid; ++b)
-                    sum += (double)host[(size_t)b * 8 + k];
+                    sum += (double)host[(size_t)b * 16 + k];
                 fprintf(f, "%s %.0f\n", names[k], sum / grid);
             }
             fprintf(f, "ctas %d frames %d\n", grid, frames);

@@ -37,7 +37,31 @@ const ModcodDef* find_modcod(int standard, int framesize, int rate)
 // such layers we compute level[j] = 1 + max(level[j'] : j' < j touches one of j's bits); check
 // nodes of equal level are independent, and running the levels in order reproduces the serial
 // result bit for bit.
-void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem)
+// Which form of the conflict layers is faster was measured per code on B200 (profiles/): split steps win
+// where a good part of the layers is order sensitive and their shared links are few (DVB-S2 3/4, 2/3 short:
+// +16..18 %), the wavefront form (tensor-memory state, warp-0 runs) where conflict layers are rare (1/2 normal)
+// or carry many shared links on high-degree check nodes (9/10 normal).
+bool choose_split(const LdpcTableDef& def)
+{
+    if (const char* env = getenv("DVBS2B200_SPLIT"))
+        return atoi(env) != 0;
+    std::vector<std::vector<int>> groups(def.q);
+    for (int c = 0; c < def.n_circ; ++c)
+        groups[def.circ[c] >> 17].push_back((int)((def.circ[c] >> 9) & 0xff));
+    int conflict_layers = 0, max_shared = 0;
+    for (auto& g : groups) {
+        std::sort(g.begin(), g.end());
+        int shared = 0;
+        for (size_t a = 0; a < g.size(); ++a)
+            if ((a && g[a] == g[a - 1]) || (a + 1 < g.size() && g[a] == g[a + 1]))
+                ++shared;
+        conflict_layers += shared > 0;
+        max_shared = std::max(max_shared, shared);
+    }
+    return max_shared <= 4 && 7 * conflict_layers >= 3 * def.q;
+}
+
+void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem, int split_arg)
 {
     const int q = def.q;
     s = Schedule();
@@ -49,6 +73,8 @@ void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem)
     }
     const int ngroups = def.K / 360;
     std::vector<int> last(ngroups * 360);
+    const bool split = split_arg < 0 ? choose_split(def) : split_arg != 0;
+    s.split = split;
     for (int i = 0; i < q; ++i) {
         auto& circ = per_layer[i];
         LayerRec& L = s.layers[i];
@@ -56,13 +82,21 @@ void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem)
         L.cnt = (uint16_t)circ.size();
         s.max_cnt = std::max(s.max_cnt, (int)circ.size());
         s.min_cnt = std::min(s.min_cnt, (int)circ.size());
-        bool conflict = false;
+        // Links whose 360-bit group carries another circulant of this layer are "shared": their bits are
+        // touched by two or more check nodes of the layer.  They go last in the layer's link order (the
+        // order of the links of a check node is immaterial to the result: minima, sign products and the
+        // per-link saturating updates are all order independent), so the private links are 0 .. cnt-n_shared-1.
+        std::vector<int> mult(ngroups, 0);
+        for (auto& ga : circ)
+            mult[ga.first]++;
+        std::stable_partition(circ.begin(), circ.end(), [&](const std::pair<int, int>& ga) { return mult[ga.first] == 1; });
+        int n_shared = 0;
         for (size_t a = 0; a < circ.size(); ++a) {
             s.edges.push_back(pack_edge(circ[a].first, circ[a].second));
-            if (a && circ[a].first == circ[a - 1].first)
-                conflict = true; // sorted by group: equal neighbours share a group
+            n_shared += mult[circ[a].first] > 1;
         }
-        L.conflict = conflict ? 1 : 0;
+        const bool conflict = n_shared > 0;
+        L.conflict = (uint16_t)n_shared;
         if (!conflict) {
             StepRec st;
             st.layer = (uint8_t)i;
@@ -87,6 +121,29 @@ void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem)
             level[j] = lv;
             depth = std::max(depth, lv);
         }
+        s.steps_per_iter += depth;
+        s.max_depth = std::max(s.max_depth, depth);
+        if (split) { // n_shared <= kMaxSharedLinks holds for all 57 tables (asserted by tests/test_host_cpu.py)
+            // One "split" step: private links of all 360 check nodes in parallel, the shared links level by
+            // level (code_tables.h).  work[] holds level[j] for j = 0..359.
+            StepRec st;
+            st.layer = (uint8_t)i;
+            st.run_len = 0;
+            st.count = (uint16_t)depth;
+            st.work_off = (uint32_t)s.order.size() | kStepSplit;
+            for (int j = 0; j < 360; ++j)
+                s.order.push_back((uint16_t)level[j]);
+            // thread count of the named barrier in front of level l: the warps with nodes in level l-1 or l
+            // (thread p = j % 180 owns node j; levels rise with j)
+            std::vector<uint32_t> warps(depth + 2, 0);
+            for (int j = 0; j < 360; ++j)
+                warps[level[j]] |= 1u << ((j % 180) / 32);
+            s.order.push_back(0);
+            for (int lv = 1; lv <= depth; ++lv)
+                s.order.push_back((uint16_t)(32 * __builtin_popcount(warps[lv - 1] | warps[lv])));
+            s.steps.push_back(st);
+            continue;
+        }
         for (int lv = 1; lv <= depth; ++lv) {
             StepRec st;
             st.layer = (uint8_t)i;
@@ -98,8 +155,6 @@ void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem)
             st.count = (uint16_t)(s.order.size() - st.work_off);
             s.steps.push_back(st);
         }
-        s.steps_per_iter += depth;
-        s.max_depth = std::max(s.max_depth, depth);
     }
 
     // ---- barrier placement ---------------------------------------------------------------------
@@ -124,7 +179,7 @@ void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem)
     const int lp_lanes = env_lp ? atoi(env_lp) : -1;
     const int w0_max = env_w0 ? atoi(env_w0) : 32;
     auto step_class = [&](const StepRec& st) {
-        if (st.count == 0)
+        if (st.count == 0 || (st.work_off & kStepSplit))
             return 0;
         const int G = group_lanes(st.layer), deg = (int)per_layer[st.layer].size() + 2;
         const int lp_warps = ((int)st.count * G + 31) / 32;
@@ -162,7 +217,9 @@ void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem)
     }
     for (size_t k = 0; k < s.steps.size(); ++k) {
         StepRec& st = s.steps[k];
-        const bool conflict_layer = st.count != 0;
+        const bool is_split = (st.work_off & kStepSplit) != 0;
+        // a split step keeps the pair mapping (thread p owns check nodes p and p+180): parity links stay private
+        const bool conflict_layer = st.count != 0 && !is_split;
         const bool sub = (st.work_off & kStepRun) != 0; // runs on a subset of the warps
         const bool inside_run = sub && st.run_len == 0;          // ordered by the run's own barrier
         std::vector<int> groups;
@@ -170,7 +227,7 @@ void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem)
             groups.push_back(ga.first);
         // conflict layers run single check nodes on arbitrary threads: their parity links are not
         // thread private, and the neighbouring layers' parity links collide with them
-        const bool prev_conflict = k > 0 && s.steps[k - 1].count != 0;
+        const bool prev_conflict = k > 0 && s.steps[k - 1].count != 0 && !(s.steps[k - 1].work_off & kStepSplit);
         bool need = false;
         for (int g : groups)
             need |= dirty_all[g] || (!inside_run && dirty_sub[g]);
@@ -186,6 +243,13 @@ void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem)
             s.barriers_per_iter++;
             clear();
         }
+        if (is_split && !need) {
+            // the named barriers of the levels are reused from one split step to the next: keep a block
+            // barrier between them and whatever ran before
+            st.work_off |= kStepBarrierBefore;
+            s.barriers_per_iter++;
+            clear();
+        }
         for (int g : groups)
             (sub ? dirty_sub : dirty_all)[g] = 1;
     }
@@ -195,7 +259,7 @@ void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem)
     if (use_tmem && s.max_cnt <= 13) { // one-word state only
         int next_col = 0;
         auto cols_needed = [&](const StepRec& st) {
-            if (st.count == 0 || (st.work_off & kStepLinkParallel))
+            if (st.count == 0 || (st.work_off & (kStepLinkParallel | kStepSplit)))
                 return 0;
             if (st.work_off & kStepRun)
                 return 1;                          // warp 0, one pass
@@ -350,6 +414,7 @@ bool build_blob(int standard, int framesize, int rate, std::vector<uint8_t>& blo
     h.max_depth = s.max_depth;
     h.uniform_cnt = (s.min_cnt == s.max_cnt) ? 1 : 0;
     h.bch_shorten = ((1u << h.gf_m) - 1) - (uint32_t)mc->nbch;
+    h.split_steps = s.split ? 1u : 0u;
 
     size_t off = sizeof(BlobHeader);
     h.smem_off = (uint32_t)off;
@@ -370,7 +435,7 @@ bool build_blob(int standard, int framesize, int rate, std::vector<uint8_t>& blo
     {
         int placed = 0, scalar_steps = 0;
         for (size_t k = 0; k < s.steps.size(); ++k) {
-            if (s.steps[k].count == 0 || (s.steps[k].work_off & kStepLinkParallel))
+            if (s.steps[k].count == 0 || (s.steps[k].work_off & (kStepLinkParallel | kStepSplit)))
                 continue;
             ++scalar_steps;
             placed += s.tcol[k] != kNoTmem;
@@ -423,7 +488,7 @@ bool validate_blob(const void* blob, size_t size, std::string& err)
               h.smem_off == sizeof(BlobHeader) && h.layer_off == h.smem_off &&
               h.edge_off == h.layer_off + sizeof(LayerRec) * (size_t)h.q &&
               (size_t)h.smem_off + h.smem_bytes <= size && h.step_off <= h.smem_off + h.smem_bytes && h.order_off <= size &&
-              h.n_steps_total == h.steps_per_iter &&
+              h.n_steps_total > 0 && h.n_steps_total <= h.steps_per_iter &&
               (size_t)h.antilog_off + gfn <= size && (size_t)h.log_off + gfn <= size &&
               (h.msg_words == 1 || h.msg_words == 2) && h.gf_m >= 14 && h.gf_m <= 16;
     if (!ok)

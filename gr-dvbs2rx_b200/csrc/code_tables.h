@@ -29,13 +29,13 @@ const ModcodDef* find_modcod(int standard, int framesize, int rate);
 
 // ---- packed blob ---------------------------------------------------------------------------
 constexpr uint32_t kBlobMagic = 0x32425344u; // "DSB2"
-constexpr uint32_t kBlobVersion = 9;
+constexpr uint32_t kBlobVersion = 10;
 
 // One per layer, 8 bytes, lives in shared memory.
 struct LayerRec {
     uint32_t edge_begin; // first circulant of the layer in edges[]
     uint16_t cnt;        // data links per check node in this layer
-    uint16_t conflict;   // 1 if two circulants of the layer share a 360-bit group
+    uint16_t conflict;   // number of shared links (circulants whose 360-bit group carries another one of this layer)
 };
 // One per circulant, 8 bytes, lives in shared memory (see pack_edge).
 struct EdgeRec {
@@ -66,7 +66,17 @@ constexpr uint32_t kStepBarrierBefore = 1u << 24;
 constexpr uint32_t kStepRun = 1u << 25;          // part of a run executed by a subset of the warps
 constexpr uint32_t kStepWarpsShift = 26;         // 3 bits: warps taking part in the run
 constexpr uint32_t kStepLinkParallel = 1u << 29; // run class: link parallel (else one node per lane)
+constexpr uint32_t kStepSplit = 1u << 30;        // whole conflict layer in one step, see below
 constexpr uint32_t kStepOffMask = (1u << 24) - 1;
+// Split step (the default for conflict layers).  Only the links into a 360-bit group that carries two
+// or more circulants of the layer ("shared" links, LayerRec::conflict of them, sorted last) are order
+// sensitive: every other bit of the layer is touched by exactly one check node.  So thread p keeps the
+// pair mapping (check nodes p and p+180): it evaluates the private links of both nodes in s16x2 like a
+// conflict-free layer, then the block walks the levels of the serial order and a node merges only its
+// shared links into its partial minima / sign product and updates those bits, then the private links
+// are updated in s16x2 again.  The dependent chain through a layer shrinks from a whole check-node
+// update per level to a 2-link merge; StepRec::count = depth, work[] holds level[j] (1-based).
+constexpr int kMaxSharedLinks = 12; // largest over the 57 tables (DVB-S2 8/9 short)
 
 // Tensor memory as scratch for the check-node state of order-sensitive layers.  Those layers are a
 // dependent chain of short steps, and the ~700-cycle L2 round trip for the state word sits on that
@@ -94,7 +104,8 @@ struct BlobHeader {
     uint32_t step_off, order_off;  // StepRec[] (inside the smem section), uint16 work[] (global)
     uint32_t antilog_off, log_off; // uint16[2^m] each: alpha^i (i < 2^m-1), log(x)
     uint32_t bch_shorten;          // s = 2^m - 1 - nbch
-    uint32_t reserved1[3];
+    uint32_t split_steps;          // 1: conflict layers are split steps (kernels of the _split build), 0: wavefront steps
+    uint32_t reserved1[2];
 };
 static_assert(sizeof(BlobHeader) % 16 == 0, "header must keep sections 16-byte aligned");
 
@@ -128,8 +139,11 @@ struct Schedule {
     std::vector<uint16_t> order; // work[]: check-node indices of the conflict steps
     std::vector<uint8_t> tcol;   // per step: first TMEM column of its state, or kNoTmem
     int max_cnt = 0, min_cnt = 1 << 30, steps_per_iter = 0, max_depth = 0, conflict_layers = 0, barriers_per_iter = 0;
+    bool split = false; // conflict layers emitted as split steps
 };
-void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem = true);
+// split: 1 / 0 force the form of the conflict layers, -1 lets choose_split() decide (env DVBS2B200_SPLIT overrides)
+void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem = true, int split = -1);
+bool choose_split(const LdpcTableDef& def);
 
 // ---- GF(2^m) / BCH host helpers --------------------------------------------------------------
 uint32_t bch_prim_poly(int framesize); // lib/bch_decoder_bb_impl.cc:58-63

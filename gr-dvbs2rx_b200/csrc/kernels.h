@@ -34,13 +34,21 @@ struct LdpcLaunch {
     // optional per-CTA cycle counters [grid][8]: load, syndrome pass, pair steps, runs, wide steps,
     // iteration-end barrier, output, total (diagnostics: DVBS2B200_PHASE_PROFILE)
     unsigned long long* prof;
+    // start-up stagger: the CTAs that share an SM (block index / sm_count apart) start stagger_ns apart, so
+    // that they do not walk the latency-bound conflict layers of the code at the same time
+    int sm_count;
+    unsigned int stagger_ns;
 };
 
 // fills the smem_* offsets of p (if non-null) and returns the dynamic shared memory size
 size_t ldpc_smem_bytes(int N, uint32_t tab_bytes, LdpcLaunch* p);
-cudaError_t ldpc_launch(const LdpcLaunch& p, int max_cnt, bool uniform, bool tmem, int grid, size_t smem, cudaStream_t stream);
+// Two builds of ldpc_kernel.cu: order-sensitive layers as split steps (_split) or as wavefront steps of whole
+// check nodes (_wavefront, with the tensor-memory state variant `tmem`); the blob says which schedule it holds.
+cudaError_t ldpc_launch_split(const LdpcLaunch& p, int max_cnt, bool uniform, bool tmem, int grid, size_t smem, cudaStream_t stream);
+cudaError_t ldpc_launch_wavefront(const LdpcLaunch& p, int max_cnt, bool uniform, bool tmem, int grid, size_t smem, cudaStream_t stream);
 // resident CTAs per SM for this code's kernel instantiation (occupancy query)
-int ldpc_ctas_per_sm(int max_cnt, bool uniform, bool tmem, size_t smem);
+int ldpc_ctas_per_sm_split(int max_cnt, bool uniform, bool tmem, size_t smem);
+int ldpc_ctas_per_sm_wavefront(int max_cnt, bool uniform, bool tmem, size_t smem);
 // true when the check-node state takes two words per node (more than 13 data links)
 bool ldpc_wide_state(int max_cnt);
 

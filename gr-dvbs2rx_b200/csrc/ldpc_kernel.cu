@@ -34,6 +34,20 @@
 
 #include "kernels.h"
 
+// This file is compiled twice (__graft_entry__.py): DVBS2_LEGACY_WAVEFRONT=0 builds the kernels whose
+// order-sensitive layers run as "split" steps, =1 the ones that run them as wavefront steps of whole check
+// nodes (with the tensor-memory state variant).  One binary with both paths inlined costs the hot
+// conflict-free pair step registers and instruction-cache hits, so they are separate kernels and the host
+// picks per code (code_tables.cc:choose_split).
+#ifndef DVBS2_LEGACY_WAVEFRONT
+#define DVBS2_LEGACY_WAVEFRONT 0
+#endif
+#if DVBS2_LEGACY_WAVEFRONT
+#define LDPC_SYM(x) x##_wavefront
+#else
+#define LDPC_SYM(x) x##_split
+#endif
+
 namespace dvbs2b200 {
 
 namespace {
@@ -168,6 +182,7 @@ __device__ __forceinline__ void tmem_st(uint32_t taddr, uint32_t v)
 struct LayerView {
     uint32_t edge_begin;
     int cnt;
+    int nshared; // links into groups that carry another circulant of the layer (sorted last)
 };
 __device__ __forceinline__ LayerView load_layer(const uint2* layers, int i)
 {
@@ -175,6 +190,7 @@ __device__ __forceinline__ LayerView load_layer(const uint2* layers, int i)
     LayerView v;
     v.edge_begin = r.x;
     v.cnt = (int)(r.y & 0xffffu);
+    v.nshared = (int)(r.y >> 16);
     return v;
 }
 
@@ -330,6 +346,394 @@ __device__ __forceinline__ int process_pair(int8_t* __restrict__ L, const uint2*
     return 0;
 }
 
+#if !DVBS2_LEGACY_WAVEFRONT
+// ---- split step: a conflict layer with the pair mapping kept (code_tables.h) ----------------------
+// Phase 1: private links of check nodes p and p+180 in s16x2 (partial minima / sign product).
+// Phase 2: the levels of the serial order; a node merges its shared links (scalar, one half of the
+//          registers) and updates those bits.  Every thread of the block takes part in the barriers.
+// Phase 3: the private links are updated with the final minima; the state word is written.
+constexpr int kMaxShared = 12; // = code_tables.h kMaxSharedLinks
+
+// Phase 2 of a split step.  The chain through the levels of a layer is what bounds the step, so per
+// level everything that does not depend on the predecessors' writes (operand addresses, old messages,
+// the partial minima of this node) is prepared BEFORE the level's barrier, and only
+// load -> vqsub -> merge minima -> vqadd -> store sits between the barrier and the hand-over to the next level.
+template <bool WIDE>
+struct SplitCtx {
+    int8_t* L;
+    const uint2* sh_edges;      // the layer's shared circulants
+    const uint16_t* level_tab;  // [360] level of node j, then [depth + 1] barrier thread counts
+    volatile int* progress;
+    int p;
+    uint32_t pkey;
+    int d0, nshared, depth;     // d0 = link index of the first shared link
+    int lvA, lvB;
+    bool active;
+    uint32_t wA, wB, sA, sB;
+    unsigned long long* prof; // diagnostics build: [8..12] = barrier wait, chain, hand-over cycles, levels, pre cycles (per warp lane 0)
+};
+
+template <int NSH>
+struct SplitNode {
+    int a[NSH > 0 ? NSH : 1];   // byte addresses of the operands
+    int old[NSH > 0 ? NSH : 1]; // old messages
+    int k0h, k1h, sxh, hsel;
+    uint32_t w, sg;
+};
+
+template <int NSH, bool WIDE>
+__device__ __forceinline__ void split_operand(const SplitCtx<WIDE>& c, const SplitNode<NSH>& n, int s, int& a, int& old)
+{
+    const int d = c.d0 + s;
+    const uint2 e = c.sh_edges[s];
+    const bool lt = e.x > c.pkey;
+    // node p is the low byte of the halfword iff (ra ^ (p < a')) == 0, ra = bit 0 of the unpack selector
+    a = (int)(e.x & 0xffffu) + 2 * c.p - (lt ? 0 : 360) + (int)(((e.y ^ (lt ? 1u : 0u)) & 1u) ^ (uint32_t)n.hsel);
+    const int mc = (d == (int)((n.w >> 12) & 31u)) ? (int)((n.w >> 6) & 63u) : (int)(n.w & 63u);
+    old = ((n.sg >> d) & 1u) ? -mc : min(mc, 31);
+}
+
+template <int NSH, bool WIDE>
+__device__ __forceinline__ void split_pre(const SplitCtx<WIDE>& c, SplitNode<NSH>& n, int hsel, uint32_t k0, uint32_t k1, uint32_t sx)
+{
+    n.hsel = hsel;
+    n.w = hsel ? c.wB : c.wA;
+    n.sg = WIDE ? (hsel ? c.sB : c.sA) : (n.w >> 17);
+    n.k0h = (int)((k0 >> (16 * hsel)) & 0xffffu);
+    n.k1h = (int)((k1 >> (16 * hsel)) & 0xffffu);
+    n.sxh = (int)(int16_t)(sx >> (16 * hsel));
+#pragma unroll
+    for (int s = 0; s < NSH; ++s)
+        split_operand<NSH, WIDE>(c, n, s, n.a[s], n.old[s]);
+}
+
+// between the barrier of the level and the hand-over: the node's shared operands are read, merged, updated
+template <int NSH, bool WIDE>
+__device__ __forceinline__ void split_chain(const SplitCtx<WIDE>& c, SplitNode<NSH>& n, uint32_t& shs_lo, uint32_t& shs_hi)
+{
+    const int sh = 16 * n.hsel;
+    if (NSH > 0) {
+        int x[NSH > 0 ? NSH : 1], mg[NSH > 0 ? NSH : 1];
+#pragma unroll
+        for (int s = 0; s < NSH; ++s)
+            x[s] = (int)c.L[n.a[s]];
+#pragma unroll
+        for (int s = 0; s < NSH; ++s) {
+            x[s] = min(max(x[s] - n.old[s], -128), 127);
+            n.sxh ^= x[s];
+            mg[s] = max(min(abs(x[s]), 127) - 1, 0);
+            const int key = mg[s] * 32 + c.d0 + s;
+            n.k1h = min(n.k1h, max(n.k0h, key));
+            n.k0h = min(n.k0h, key);
+        }
+        const int min0 = n.k0h >> 5, min1 = n.k1h >> 5;
+#pragma unroll
+        for (int s = 0; s < NSH; ++s) {
+            const int m = min0 + min1 - min(mg[s], min1);
+            const bool neg = ((n.sxh ^ x[s]) < 0);
+            c.L[n.a[s]] = (int8_t)min(max(x[s] + (neg ? -m : m), -128), 127);
+            const int d = c.d0 + s;
+            const uint32_t bit = (neg ? 1u : 0u) << ((d & 15) + sh);
+            if (!WIDE || d < 16)
+                shs_lo |= bit;
+            else
+                shs_hi |= bit;
+        }
+    } else {
+#pragma unroll 1
+        for (int s = 0; s < c.nshared; ++s) {
+            int a, old;
+            split_operand<NSH, WIDE>(c, n, s, a, old);
+            const int x = min(max((int)c.L[a] - old, -128), 127);
+            n.sxh ^= x;
+            const int key = max(min(abs(x), 127) - 1, 0) * 32 + c.d0 + s;
+            n.k1h = min(n.k1h, max(n.k0h, key));
+            n.k0h = min(n.k0h, key);
+        }
+        const int min0 = n.k0h >> 5, min1 = n.k1h >> 5;
+#pragma unroll 1
+        for (int s = 0; s < c.nshared; ++s) {
+            int a, old;
+            split_operand<NSH, WIDE>(c, n, s, a, old); // the operands are still unmodified: each is written once, below
+            const int x = min(max((int)c.L[a] - old, -128), 127);
+            const int m = min0 + min1 - min(max(min(abs(x), 127) - 1, 0), min1);
+            const bool neg = ((n.sxh ^ x) < 0);
+            c.L[a] = (int8_t)min(max(x + (neg ? -m : m), -128), 127);
+            const int d = c.d0 + s;
+            const uint32_t bit = (neg ? 1u : 0u) << ((d & 15) + sh);
+            if (!WIDE || d < 16)
+                shs_lo |= bit;
+            else
+                shs_hi |= bit;
+        }
+    }
+}
+
+__device__ __forceinline__ void split_writeback(int hsel, int k0h, int k1h, int sxh, uint32_t& k0, uint32_t& k1, uint32_t& sx)
+{
+    const uint32_t keep = hsel ? 0x0000ffffu : 0xffff0000u;
+    k0 = (k0 & keep) | ((uint32_t)k0h << (16 * hsel));
+    k1 = (k1 & keep) | ((uint32_t)k1h << (16 * hsel));
+    sx = (sx & keep) | (((uint32_t)sxh & 0xffffu) << (16 * hsel));
+}
+
+// Levels rise with j, so the nodes of a warp sit in two contiguous level ranges (nodes p, nodes p+180).
+// A warp only takes part in the levels it has nodes in.  Level l is entered through named barrier
+// 1 + l % 15 whose participants are the warps with nodes in level l-1 (their writes must be visible:
+// they arrive, or sync if they also have nodes in level l) and in level l (they sync); the host
+// precomputed the thread count of each barrier (level_tab[360 + l]).
+// Not inlined: one copy per (NSH, WIDE) serves every kernel instantiation, and the register allocation of the
+// hot conflict-free pair step is not burdened with this code.
+template <int NSH, bool WIDE>
+__device__ __noinline__ void split_levels(const SplitCtx<WIDE>* cp, uint32_t* io)
+{
+    const SplitCtx<WIDE> c = *cp;
+    uint32_t k0 = io[0], k1 = io[1], sx = io[2], shs_lo = 0, shs_hi = 0;
+    const int loA = (int)__reduce_min_sync(0xffffffffu, c.active ? (unsigned)c.lvA : 0xffffu);
+    const int hiA = (int)__reduce_max_sync(0xffffffffu, c.active ? (unsigned)c.lvA : 0u);
+    const int loB = (int)__reduce_min_sync(0xffffffffu, c.active ? (unsigned)c.lvB : 0xffffu);
+    const int hiB = (int)__reduce_max_sync(0xffffffffu, c.active ? (unsigned)c.lvB : 0u);
+    auto has_nodes = [&](int l) { return (l >= loA && l <= hiA) || (l >= loB && l <= hiB); };
+    int cnt_cur = (int)__ldg(c.level_tab + 360 + loA);
+#ifdef DVBS2_SKIP_PHASE2 // timing experiment only: results are wrong
+    for (int lvl = loA; lvl < loA; ++lvl) {
+#else
+    for (int lvl = loA; lvl <= hiB; ++lvl) {
+#endif
+        if (!has_nodes(lvl)) {
+            lvl = loB - 1; // the gap between the two ranges
+            cnt_cur = (int)__ldg(c.level_tab + 360 + loB);
+            continue;
+        }
+#ifdef DVBS2_PHASE_PROFILE
+        const long long tp0 = clock64();
+#endif
+        const bool next_mine = has_nodes(lvl + 1);
+        const int cnt_next = (int)__ldg(c.level_tab + 360 + min(lvl + 1, c.depth));
+        const bool doA = c.lvA == lvl, doB = c.lvB == lvl;
+        SplitNode<NSH> n;
+        if (doA || doB)
+            split_pre<NSH, WIDE>(c, n, doA ? 0 : 1, k0, k1, sx);
+#ifdef DVBS2_PHASE_PROFILE
+        const long long tp1 = clock64();
+#endif
+        if (lvl > 1) {
+            // A warp may get here long before the chain does.  The barrier id is shared with level
+            // lvl - 15: wait until that one has completed (progress = highest level known complete).
+            if (lvl > 15)
+                while (*c.progress < lvl - 16)
+                    __nanosleep(64);
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + lvl % 15), "r"(cnt_cur) : "memory");
+        }
+#ifdef DVBS2_PHASE_PROFILE
+        const long long tp2 = clock64();
+#endif
+        if (doA || doB)
+            split_chain<NSH, WIDE>(c, n, shs_lo, shs_hi);
+        if (doA && doB) { // both nodes of the thread in one level (shallow layers only)
+            split_writeback(0, n.k0h, n.k1h, n.sxh, k0, k1, sx);
+            split_pre<NSH, WIDE>(c, n, 1, k0, k1, sx);
+            split_chain<NSH, WIDE>(c, n, shs_lo, shs_hi);
+        }
+        // hand over to level lvl + 1: if this warp has nodes there it syncs at the top of the loop
+#ifdef DVBS2_PHASE_PROFILE
+        const long long tp3 = clock64();
+#endif
+        if (lvl < c.depth && !next_mine)
+            asm volatile("bar.arrive %0, %1;" ::"r"(1 + (lvl + 1) % 15), "r"(cnt_next) : "memory");
+        if (lvl > 1 && (threadIdx.x & 31) == 0)
+            atomicMax(const_cast<int*>(c.progress), lvl - 1);
+        if (doA || doB)
+            split_writeback(n.hsel, n.k0h, n.k1h, n.sxh, k0, k1, sx);
+        cnt_cur = cnt_next;
+#ifdef DVBS2_PHASE_PROFILE
+        if (c.prof && (threadIdx.x & 31) == 0) {
+            const long long tp4 = clock64();
+            atomicAdd(c.prof + 8, (unsigned long long)(tp2 - tp1));
+            atomicAdd(c.prof + 9, (unsigned long long)(tp3 - tp2));
+            atomicAdd(c.prof + 10, (unsigned long long)(tp4 - tp3));
+            atomicAdd(c.prof + 11, 1ull);
+            atomicAdd(c.prof + 12, (unsigned long long)(tp1 - tp0));
+        }
+#endif
+    }
+    io[0] = k0, io[1] = k1, io[2] = sx, io[3] = shs_lo, io[4] = shs_hi;
+}
+
+template <int CNT_MAX, bool UNIFORM, bool WIDE, bool SELF_CHECK>
+__device__ __noinline__ int process_split(int8_t* __restrict__ L, const uint2* __restrict__ edges, const LayerView lv, int layer,
+                                             int p, bool active, int K, int q, uint32_t wA, uint32_t wB, uint32_t sA, uint32_t sB,
+                                             uint32_t* __restrict__ msg_out, uint64_t pol, int depth, const uint16_t* __restrict__ level_tab,
+                                             volatile int* progress, unsigned long long* prof = nullptr)
+{
+    constexpr int DEG_MAX = CNT_MAX + 2;
+    const bool first = (layer == 0 && p == 0);
+    const int half = kPairs * q;
+    const int npriv = lv.cnt - lv.nshared; // private data links: d - 2 < npriv
+    int lvA = 0, lvB = 0;
+    if (active) {
+        lvA = (int)__ldg(level_tab + p);
+        lvB = (int)__ldg(level_tab + p + kPairs);
+    }
+    const uint32_t m0 = (wA & 63u) | ((wB & 63u) << 16);
+    const uint32_t m1 = ((wA >> 6) & 63u) | (((wB >> 6) & 63u) << 16);
+    const uint32_t x01 = m0 ^ m1;
+    const uint32_t argA = (wA >> 12) & 31u, argB = (wB >> 12) & 31u;
+    uint32_t hot_lo, hot_hi = 0, nsg_lo, nsg_hi = 0;
+    if (!WIDE) {
+        hot_lo = (1u << argA) | (0x10000u << argB);
+        nsg_lo = ~((wA >> 17) | ((wB >> 17) << 16));
+    } else {
+        hot_lo = ((1u << argA) & 0xffffu) | (((1u << argB) & 0xffffu) << 16);
+        hot_hi = ((1u << argA) >> 16) | ((1u << argB) & 0xffff0000u);
+        nsg_lo = ~((sA & 0xffffu) | (sB << 16));
+        nsg_hi = ~((sA >> 16) | (sB & 0xffff0000u));
+    }
+    int adr[DEG_MAX];
+    uint32_t sel[DEG_MAX];
+    uint32_t v[DEG_MAX], mag[DEG_MAX];
+    const int c = q * p + layer;
+    adr[0] = K + 2 * c;
+    sel[0] = 0x9180u | (0x4420u << 16);
+    adr[1] = first ? K + 2 * (half - 1) : K + 2 * c - 2;
+    sel[1] = first ? (0x8091u | (0x4402u << 16)) : sel[0];
+    const uint32_t pkey = ((uint32_t)p << 16) | 0xffffu;
+#pragma unroll
+    for (int d = 0; d < CNT_MAX; ++d) {
+        if (UNIFORM || d < lv.cnt) {
+            const uint2 e = edges[lv.edge_begin + d];
+            const bool lt = e.x > pkey;
+            adr[d + 2] = (int)(e.x & 0xffffu) + 2 * p - (lt ? 0 : 360);
+            sel[d + 2] = lt ? (e.y ^ 0x00221111u) : e.y;
+        } else {
+            adr[d + 2] = 0;
+            sel[d + 2] = 0;
+        }
+    }
+    const uint32_t n0p = vsub(0u, vmin(m0, h2(31))), n1p = vsub(0u, vmin(m1, h2(31)));
+    const uint32_t nx01p = n0p ^ n1p;
+    uint32_t k0 = h2(0x7fff), k1 = h2(0x7fff), sx = 0;
+    if (active) {
+#pragma unroll
+        for (int d = 0; d < DEG_MAX; ++d) {
+            const bool live = (d < 2) || (d - 2 < npriv);
+            if (live) {
+                const uint32_t raw = *reinterpret_cast<const uint16_t*>(L + adr[d]);
+                const uint32_t l = prmt(raw, 0, sel[d]);
+                const uint32_t hot = (!WIDE || d < 16) ? hot_lo : hot_hi;
+                const uint32_t nsg = (!WIDE || d < 16) ? nsg_lo : nsg_hi;
+                const uint32_t im = signmask(hot << (15 - (d & 15)));
+                const uint32_t nm = signmask(nsg << (15 - (d & 15)));
+                const uint32_t xa = vadd(l, n0p ^ (nx01p & im));
+                const uint32_t xb = vadd(l, m0 ^ (x01 & im));
+                uint32_t x = vmin(vmax(bsel(nm, xa, xb), h2(-128)), h2(127));
+                if (d == 1 && first)
+                    x &= 0xffff0000u;
+                v[d] = x;
+                sx ^= x;
+                const uint32_t mg = vmin(vmax(vmax(vadd(x, h2(-1)), ~x), 0u), h2(126));
+                mag[d] = mg;
+                uint32_t key = imad(mg, 32u, h2(d));
+                if (d == 1 && first)
+                    key |= 0x00007fffu;
+                k1 = vmin(k1, vmax(k0, key));
+                k0 = vmin(k0, key);
+            } else {
+                v[d] = 0;
+                mag[d] = 0;
+            }
+        }
+    }
+    // ---- phase 2: shared links, level by level ----
+    // Levels rise with j, so the nodes of a warp sit in two contiguous level ranges (nodes p, nodes p+180).
+    // A warp only takes part in the levels it has nodes in.  Level l is entered through named barrier
+    // 1 + l % 15 whose participants are the warps with nodes in level l-1 (their writes must be visible:
+    // they arrive, or sync if they also have nodes in level l) and in level l (they sync); the host
+    // precomputed the thread count of each barrier (level_tab[360 + l]).
+    uint32_t shs_lo = 0, shs_hi = 0; // new sign bits of the shared links, same layout as newsg_lo / newsg_hi
+    {
+        SplitCtx<WIDE> cx = { L, edges + lv.edge_begin + npriv, level_tab, progress, p, pkey, 2 + npriv, lv.nshared, depth, lvA, lvB,
+                              active, wA, wB, sA, sB, prof };
+        uint32_t io[5] = { k0, k1, sx, 0u, 0u };
+        switch (lv.nshared) { // compile-time link counts for the common cases, a rolled loop for the rest
+        case 2: split_levels<2, WIDE>(&cx, io); break;
+        case 3: split_levels<3, WIDE>(&cx, io); break;
+        case 4: split_levels<4, WIDE>(&cx, io); break;
+        default: split_levels<0, WIDE>(&cx, io); break;
+        }
+        k0 = io[0], k1 = io[1], sx = io[2], shs_lo = io[3], shs_hi = io[4];
+    }
+    if (SELF_CHECK)
+        __syncthreads(); // the shared bits are re-read below, final only after the last level
+    if (!active)
+        return 0;
+    // ---- phase 3: private links ----
+    const uint32_t min0 = (k0 >> 5) & 0x07ff07ffu;
+    const uint32_t min1 = (k1 >> 5) & 0x07ff07ffu;
+    const uint32_t s01 = vadd(min0, min1);
+    const uint32_t s01p1 = vadd(s01, h2(1)), ns01 = vsub(0u, s01);
+    uint32_t newsg_lo = 0, newsg_hi = 0, syn = 0, zer = 0;
+#pragma unroll
+    for (int dd = 0; dd < DEG_MAX; ++dd) {
+        const int d = DEG_MAX - 1 - dd;
+        const bool live = (d < 2) || (d - 2 < npriv);
+        if (!WIDE || d < 16)
+            newsg_lo = vadd(newsg_lo, newsg_lo);
+        else
+            newsg_hi = vadd(newsg_hi, newsg_hi);
+        if (live) {
+            const uint32_t t = vmin(mag[d], min1);
+            const uint32_t np = vadd(vadd(v[d], s01p1), ~t);
+            const uint32_t nn = vadd(vadd(v[d], ns01), t);
+            const uint32_t ng = signmask(sx ^ v[d]);
+            const uint32_t nl = vmin(vmax(bsel(ng, nn, np), h2(-128)), h2(127));
+            const uint32_t packed = prmt(nl, 0, sel[d] >> 16);
+            if (d == 1 && first)
+                L[adr[d]] = (int8_t)(nl >> 16);
+            else
+                *reinterpret_cast<uint16_t*>(L + adr[d]) = (uint16_t)packed;
+            const uint32_t bit = ng & 0x00010001u;
+            if (!WIDE || d < 16)
+                newsg_lo = vadd(newsg_lo, bit);
+            else
+                newsg_hi = vadd(newsg_hi, bit);
+            if (SELF_CHECK) {
+                uint32_t nlc = nl;
+                if (d == 1 && first)
+                    nlc = (nl & 0xffff0000u) | 1u;
+                syn ^= nlc;
+                zer |= vsub(nlc, h2(1)) & ~nlc;
+            }
+        } else if (SELF_CHECK && (UNIFORM || d - 2 < lv.cnt)) {
+            const uint32_t raw = *reinterpret_cast<const uint16_t*>(L + adr[d]);
+            const uint32_t nlc = prmt(raw, 0, sel[d]);
+            syn ^= nlc;
+            zer |= vsub(nlc, h2(1)) & ~nlc;
+        }
+    }
+    newsg_lo |= shs_lo;
+    newsg_hi |= shs_hi;
+    const uint32_t c0 = vmin(min0, h2(32)), c1 = vmin(min1, h2(32));
+    uint32_t nA = (c0 & 0xffffu) | ((c1 & 0xffffu) << 6) | ((k0 & 31u) << 12);
+    uint32_t nB = (c0 >> 16) | ((c1 >> 16) << 6) | (((k0 >> 16) & 31u) << 12);
+    if (!WIDE) {
+        nA |= (newsg_lo & 0x7fffu) << 17;
+        nB |= ((newsg_lo >> 16) & 0x7fffu) << 17;
+        stg_hint(reinterpret_cast<uint2*>(msg_out), make_uint2(nA, nB), pol);
+    } else {
+        const uint32_t tA = (newsg_lo & 0xffffu) | (newsg_hi << 16);
+        const uint32_t tB = (newsg_lo >> 16) | (newsg_hi & 0xffff0000u);
+        stg_hint(reinterpret_cast<uint4*>(msg_out), make_uint4(nA, nB, tA, tB), pol);
+    }
+    if (SELF_CHECK)
+        return (int)(((syn | zer) & 0x80008000u) != 0);
+    return 0;
+}
+
+#endif // !DVBS2_LEGACY_WAVEFRONT
+
+// ---- legacy wavefront paths (whole check nodes level by level; -DDVBS2_LEGACY_WAVEFRONT=1) --------
+#if DVBS2_LEGACY_WAVEFRONT
 // ---- one check node j of a conflict layer (scalar, same arithmetic) -------------------------------
 template <int CNT_MAX, bool UNIFORM, bool WIDE, bool SELF_CHECK>
 __device__ __forceinline__ int process_cn(int8_t* __restrict__ L, const uint2* __restrict__ edges, const LayerView& lv, int layer,
@@ -647,6 +1051,8 @@ __device__ __noinline__ int scalar_run(int8_t* __restrict__ L, const uint2* __re
     return self_bad;
 }
 
+#endif // DVBS2_LEGACY_WAVEFRONT
+
 // lib/ldpc_decoder/layered_decoder.hh:32-49 for the pair (p, p+180): unsatisfied if the sign product
 // is not +, and a zero LLR counts as unsatisfied (vsign(.,0) = 0, test is "> 0").
 template <int CNT_MAX, bool UNIFORM>
@@ -692,6 +1098,7 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + p.smem_bar_off);
     __shared__ int s_group_bad;
     __shared__ uint32_t s_tmem_base;
+    __shared__ int s_progress; // split steps: highest level of the current layer known to be complete
 
     const int tid = threadIdx.x;
     const int N = p.N, K = p.K, q = p.q, R = p.R;
@@ -740,6 +1147,12 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
 #else
 #define LAP(slot) ((void)0)
 #endif
+    if (p.stagger_ns && p.group <= 1) {
+        const unsigned int slot = blockIdx.x / (unsigned int)p.sm_count;
+        const long long t_end = clock64() + (long long)slot * p.stagger_ns * 2; // ~2 cycles per ns
+        while (clock64() < t_end)
+            __nanosleep(1000);
+    }
     for (int f = blockIdx.x; f < p.frames; f += gridDim.x) {
         // ---- streaming input: wait until the host->device copy of this frame's chunk has landed ----
         if (p.ready) {
@@ -822,7 +1235,7 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
             uint32_t wA = 0, wB = 0, sA = 0, sB = 0;
             // state words of a pair step, requested from L2 one step ahead of their use
             auto prefetch = [&](uint2 s) {
-                if ((s.x >> 16) == 0 && tid < kPairs && !zero_state) {
+                if (((s.x >> 16) == 0 || ((s.y >> 30) & 1u)) && tid < kPairs && !zero_state) {
                     const uint32_t* m = msg + ((size_t)(s.x & 0xffu) * kPairs + tid) * 2 * MW;
                     if (!WIDE) {
                         const uint2 t = ldg_hint(reinterpret_cast<const uint2*>(m), pol_keep);
@@ -841,6 +1254,7 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
                 const uint32_t work_off = st.y & 0x00ffffffu;
                 const bool barrier_before = (st.y >> 24) & 1u, is_run = (st.y >> 25) & 1u, link_parallel = (st.y >> 29) & 1u;
                 const int sub_warps = (int)((st.y >> 26) & 7u);
+                const bool is_split = (st.y >> 30) & 1u;
                 const LayerView lv = load_layer(layers, layer);
                 const int next = s + (is_run ? run_len : 1);
                 const bool last = (next == p.n_steps);
@@ -849,9 +1263,17 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
                     st = steps[next];
                     prefetch(st); // the next layer's state words travel while this one computes
                 }
-                // a block barrier only where another thread's writes are read (code_tables.cc)
+                // a block barrier only where another thread's writes are read (code_tables.cc); every split
+                // step has one (its named barriers and s_progress are reused from one to the next)
                 if (barrier_before)
                     __syncthreads();
+#if !DVBS2_LEGACY_WAVEFRONT
+                if (is_split) {
+                    if (tid == 0)
+                        s_progress = 0;
+                    __syncthreads();
+                }
+#endif
                 if (count == 0) {
                     if (tid < kPairs) {
                         uint32_t* mo = msg + ((size_t)layer * kPairs + tid) * 2 * MW;
@@ -860,7 +1282,20 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
                         else
                             process_pair<CNT_MAX, UNIFORM, WIDE, false>(L, edges, lv, layer, tid, K, q, cA, cB, csA, csB, mo, pol_keep);
                     }
-                } else if (is_run) {
+                }
+#if !DVBS2_LEGACY_WAVEFRONT
+                else if (is_split) {
+                    // conflict layer, pair mapping kept: private links in s16x2, shared links level by level
+                    uint32_t* mo = msg + ((size_t)layer * kPairs + (tid < kPairs ? tid : 0)) * 2 * MW;
+                    if (last)
+                        self_bad |= process_split<CNT_MAX, UNIFORM, WIDE, true>(L, edges, lv, layer, tid, tid < kPairs, K, q, cA, cB, csA, csB, mo,
+                                                                                pol_keep, count, work + work_off, &s_progress, p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr);
+                    else
+                        process_split<CNT_MAX, UNIFORM, WIDE, false>(L, edges, lv, layer, tid, tid < kPairs, K, q, cA, cB, csA, csB, mo, pol_keep,
+                                                                     count, work + work_off, &s_progress, p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr);
+                }
+#else
+                else if (is_run) {
                     // run of narrow wavefront levels on the first sub_warps warps; the other warps move on
                     if (tid < sub_warps * 32) {
                         if (link_parallel)
@@ -902,6 +1337,7 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
                         }
                     }
                 }
+#endif
                 LAP(count == 0 ? 2 : (is_run ? 3 : 4));
                 s = next;
             }
@@ -965,7 +1401,7 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
     if (p.prof && tid == 0) {
         t_phase[7] = (unsigned long long)(clock64() - t_kernel);
         for (int k = 0; k < 8; ++k)
-            p.prof[(size_t)blockIdx.x * 8 + k] = t_phase[k];
+            p.prof[(size_t)blockIdx.x * 16 + k] = t_phase[k];
     }
 #endif
 }
@@ -1017,6 +1453,7 @@ int occupancy_one(size_t smem)
 
 } // namespace
 
+#if !DVBS2_LEGACY_WAVEFRONT // shared helpers live in one of the two translation units
 namespace {
 __global__ void flag_kernel(unsigned int* flag, unsigned int value)
 {
@@ -1044,36 +1481,44 @@ size_t ldpc_smem_bytes(int N, uint32_t tab_bytes, LdpcLaunch* p)
     return off;
 }
 
+bool ldpc_wide_state(int max_cnt) { return max_cnt > 13; }
+#endif
+
 // Kernel instantiations.  Codes whose layers all have the same number of data links per check node
 // (every DVB-S2 normal-frame table) get the link count as a compile-time constant: no predication,
 // no dead link slots.  The rest take the predicated variant of the next size up.  The narrow state
 // word holds 15 sign bits (<= 13 data links), above that the wide (two-word) state is used.
-#define DVBS2_DISPATCH(CALL)                                                   \
-    if (uniform) {                                                             \
-        switch (max_cnt) {                                                     \
-        case 2: return tmem ? CALL(2, true, false, true) : CALL(2, true, false, false);   \
-        case 3: return tmem ? CALL(3, true, false, true) : CALL(3, true, false, false);   \
-        case 4: return tmem ? CALL(4, true, false, true) : CALL(4, true, false, false);   \
-        case 5: return tmem ? CALL(5, true, false, true) : CALL(5, true, false, false);   \
-        case 7: return tmem ? CALL(7, true, false, true) : CALL(7, true, false, false);   \
-        case 8: return tmem ? CALL(8, true, false, true) : CALL(8, true, false, false);   \
-        case 9: return tmem ? CALL(9, true, false, true) : CALL(9, true, false, false);   \
-        case 11: return tmem ? CALL(11, true, false, true) : CALL(11, true, false, false); \
-        case 12: return tmem ? CALL(12, true, false, true) : CALL(12, true, false, false); \
-        case 16: return CALL(16, true, true, false);                           \
-        case 20: return CALL(20, true, true, false);                           \
-        case 25: return CALL(25, true, true, false);                           \
-        case 28: return CALL(28, true, true, false);                           \
-        default: break;                                                        \
-        }                                                                      \
-    }                                                                          \
-    if (max_cnt <= 5) return tmem ? CALL(5, false, false, true) : CALL(5, false, false, false);    \
-    if (max_cnt <= 9) return tmem ? CALL(9, false, false, true) : CALL(9, false, false, false);    \
-    if (max_cnt <= 13) return tmem ? CALL(13, false, false, true) : CALL(13, false, false, false); \
-    if (max_cnt <= 18) return CALL(18, false, true, false);                    \
+#if DVBS2_LEGACY_WAVEFRONT
+#define DVBS2_TM(CALL, C, U) (tmem ? CALL(C, U, false, true) : CALL(C, U, false, false))
+#else
+#define DVBS2_TM(CALL, C, U) CALL(C, U, false, false)
+#endif
+#define DVBS2_DISPATCH(CALL)                                   \
+    if (uniform) {                                             \
+        switch (max_cnt) {                                     \
+        case 2: return DVBS2_TM(CALL, 2, true);                \
+        case 3: return DVBS2_TM(CALL, 3, true);                \
+        case 4: return DVBS2_TM(CALL, 4, true);                \
+        case 5: return DVBS2_TM(CALL, 5, true);                \
+        case 7: return DVBS2_TM(CALL, 7, true);                \
+        case 8: return DVBS2_TM(CALL, 8, true);                \
+        case 9: return DVBS2_TM(CALL, 9, true);                \
+        case 11: return DVBS2_TM(CALL, 11, true);              \
+        case 12: return DVBS2_TM(CALL, 12, true);              \
+        case 16: return CALL(16, true, true, false);           \
+        case 20: return CALL(20, true, true, false);           \
+        case 25: return CALL(25, true, true, false);           \
+        case 28: return CALL(28, true, true, false);           \
+        default: break;                                        \
+        }                                                      \
+    }                                                          \
+    if (max_cnt <= 5) return DVBS2_TM(CALL, 5, false);         \
+    if (max_cnt <= 9) return DVBS2_TM(CALL, 9, false);         \
+    if (max_cnt <= 13) return DVBS2_TM(CALL, 13, false);       \
+    if (max_cnt <= 18) return CALL(18, false, true, false);    \
     if (max_cnt <= 28) return CALL(28, false, true, false);
 
-cudaError_t ldpc_launch(const LdpcLaunch& p, int max_cnt, bool uniform, bool tmem, int grid, size_t smem, cudaStream_t stream)
+cudaError_t LDPC_SYM(ldpc_launch)(const LdpcLaunch& p, int max_cnt, bool uniform, bool tmem, int grid, size_t smem, cudaStream_t stream)
 {
 #define CALL(C, U, W, T) launch_one<C, U, W, T>(p, grid, smem, stream)
     DVBS2_DISPATCH(CALL)
@@ -1081,14 +1526,14 @@ cudaError_t ldpc_launch(const LdpcLaunch& p, int max_cnt, bool uniform, bool tme
     return cudaErrorInvalidValue;
 }
 
-int ldpc_ctas_per_sm(int max_cnt, bool uniform, bool tmem, size_t smem)
+int LDPC_SYM(ldpc_ctas_per_sm)(int max_cnt, bool uniform, bool tmem, size_t smem)
 {
+    if (tmem && !DVBS2_LEGACY_WAVEFRONT)
+        return 0; // the tensor-memory variant belongs to the legacy wavefront paths
 #define CALL(C, U, W, T) occupancy_one<C, U, W, T>(smem)
     DVBS2_DISPATCH(CALL)
 #undef CALL
     return 0;
 }
-
-bool ldpc_wide_state(int max_cnt) { return max_cnt > 13; }
 
 } // namespace dvbs2b200

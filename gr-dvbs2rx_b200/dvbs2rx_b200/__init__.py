@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libdvbs2_b200.so")
+# DVBS2B200_LIB: another build of the same library (diagnostics builds such as -DDVBS2_PHASE_PROFILE)
+LIB_PATH = os.environ.get("DVBS2B200_LIB") or os.path.join(os.path.dirname(_HERE), "libdvbs2_b200.so")
 
 # ---- enums (dvb_config.h) -----------------------------------------------------------------------
 STANDARD_DVBS2, STANDARD_DVBT2 = 0, 1

@@ -671,3 +671,171 @@ void orc_demap_8psk(const float* iq, int n_syms, float n0, int rate, int8_t* llr
         llr[r2 + j] = b2;
     }
 }
+
+/* ------------------------------------------------------------------------------------- */
+/* BB layer: descrambler and deheader                                   */
+/* ------------------------------------------------------------------------------------- */
+/* lib/bbdescrambler_bb_impl.cc:51-65: the PRBS 1 + x^14 + x^15, register loaded with
+ * 100101010000000, one bit per BBFRAME bit, MSB first inside a byte. */
+void orc_bb_prbs(uint8_t* seq, int nbytes)
+{
+    memset(seq, 0, (size_t)nbytes);
+    int sr = 0x4A80;
+    for (int i = 0; i < nbytes * 8; i++) {
+        int b = ((sr) ^ (sr >> 1)) & 1;
+        seq[i / 8] |= (uint8_t)(b << (7 - (i % 8)));
+        sr >>= 1;
+        if (b)
+            sr |= 0x4000;
+    }
+}
+
+/* lib/bbdescrambler_bb_impl.cc:67-82: every BBFRAME of kbch/8 bytes XORed with the same sequence */
+void orc_bb_descramble(const uint8_t* in, int frames, int kbch_bytes, uint8_t* out)
+{
+    uint8_t* seq = (uint8_t*)malloc((size_t)kbch_bytes);
+    orc_bb_prbs(seq, kbch_bytes);
+    for (int f = 0; f < frames; ++f)
+        for (int j = 0; j < kbch_bytes; ++j)
+            out[(size_t)f * kbch_bytes + j] = in[(size_t)f * kbch_bytes + j] ^ seq[j];
+    free(seq);
+}
+
+/* CRC-8 with g(x) = x^8+x^7+x^6+x^4+x^2+1 (lib/bbdeheader_bb_impl.cc:55).  The reference takes the
+ * remainder of the byte string itself (lib/gf_util.h:219-262, no x^8 padding) and tests it for zero
+ * (lib/bbdeheader_bb_impl.cc:138-142); since g(0) = 1, rem(y) = 0 <=> rem(y * x^8) = 0, which is
+ * what the byte-wise table recursion below yields. */
+static uint8_t crc8_tab[256];
+static int crc8_ready = 0;
+static void crc8_init(void)
+{
+    for (int i = 0; i < 256; ++i) {
+        uint32_t r = (uint32_t)i << 8;
+        for (int b = 15; b >= 8; --b)
+            if (r & (1u << b))
+                r ^= 0x1D5u << (b - 8);
+        crc8_tab[i] = (uint8_t)r;
+    }
+    crc8_ready = 1;
+}
+uint8_t orc_crc8(const uint8_t* in, int size)
+{
+    if (!crc8_ready)
+        crc8_init();
+    uint8_t c = 0;
+    for (int i = 0; i < size; ++i)
+        c = crc8_tab[c ^ in[i]];
+    return c;
+}
+
+struct orc_bbdeheader {
+    unsigned kbch_bytes, max_dfl; /* max_dfl in bits */
+    int synched;
+    unsigned partial_ts_bytes;
+    uint8_t partial_pkt[188];
+    uint64_t packet_cnt, error_cnt, bbframe_cnt, bbframe_drop_cnt, bbframe_gap_cnt;
+};
+
+/* lib/bbdeheader_bb_impl.cc:40-61 */
+orc_bbdeheader* orc_bbdeheader_create(int kbch)
+{
+    orc_bbdeheader* h = (orc_bbdeheader*)calloc(1, sizeof(*h));
+    h->kbch_bytes = (unsigned)kbch / 8;
+    h->max_dfl = (unsigned)kbch - 80;
+    return h;
+}
+void orc_bbdeheader_destroy(orc_bbdeheader* h) { free(h); }
+void orc_bbdeheader_counters(const orc_bbdeheader* h, uint64_t* out5)
+{
+    out5[0] = h->packet_cnt;
+    out5[1] = h->error_cnt;
+    out5[2] = h->bbframe_cnt;
+    out5[3] = h->bbframe_drop_cnt;
+    out5[4] = h->bbframe_gap_cnt;
+}
+
+/* lib/bbdeheader_bb_impl.cc:76-136: integrity check, field extraction, validation */
+static int bb_parse_header(const orc_bbdeheader* h, const uint8_t* in, unsigned* dfl, unsigned* syncd)
+{
+    if (orc_crc8(in, 10) != 0)
+        return 0;
+    unsigned upl = ((unsigned)in[2] << 8) | in[3];
+    *dfl = ((unsigned)in[4] << 8) | in[5];
+    *syncd = ((unsigned)in[7] << 8) | in[8];
+    if (*dfl > h->max_dfl)
+        return 0;
+    if (*dfl % 8 != 0)
+        return 0;
+    if (*syncd > *dfl)
+        return 0;
+    if (upl != 188 * 8)
+        return 0;
+    if (*syncd % 8 != 0)
+        return 0;
+    return 1;
+}
+
+/* lib/bbdeheader_bb_impl.cc:144-261 for `frames` whole BBFRAMEs (descrambled); returns bytes produced.
+ * One deviation, where the reference has undefined behaviour: on a re-synchronisation with
+ * syncd/8 + 1 > dfl/8 its unsigned `df_remaining` wraps and it reads far past the BBFRAME
+ * (:203-209); here such a frame yields nothing (df_remaining = 0). */
+long orc_bbdeheader_work(orc_bbdeheader* h, const uint8_t* in, int frames, uint8_t* out)
+{
+    long produced = 0;
+    for (int i = 0; i < frames; ++i) {
+        const uint8_t* frame = in + (size_t)i * h->kbch_bytes;
+        unsigned dfl = 0, syncd = 0;
+        const int valid = bb_parse_header(h, frame, &dfl, &syncd);
+        h->bbframe_cnt++;
+        if (!valid) {
+            h->synched = 0;
+            h->bbframe_drop_cnt++;
+            continue;
+        }
+        const uint8_t* p = frame + 10;
+        unsigned df_remaining = dfl / 8;
+        if (h->partial_ts_bytes > 0 && (syncd / 8) != 188 - 1 - h->partial_ts_bytes) {
+            h->synched = 0;
+            h->bbframe_gap_cnt++;
+        }
+        if (!h->synched) {
+            unsigned skip = syncd / 8 + 1;
+            if (skip > df_remaining)
+                skip = df_remaining; /* reference: unsigned wrap, out-of-bounds reads */
+            p += skip;
+            df_remaining -= skip;
+            h->synched = 1;
+            h->partial_ts_bytes = 0;
+        }
+        while (df_remaining >= 188) {
+            const uint8_t* packet;
+            if (h->partial_ts_bytes > 0) {
+                unsigned remaining = 188 - h->partial_ts_bytes;
+                memcpy(h->partial_pkt + h->partial_ts_bytes, p, remaining);
+                h->partial_ts_bytes = 0;
+                p += remaining;
+                df_remaining -= remaining;
+                packet = h->partial_pkt;
+            } else {
+                packet = p;
+                p += 188;
+                df_remaining -= 188;
+            }
+            const int crc_valid = orc_crc8(packet, 188) == 0;
+            out[0] = 0x47;
+            memcpy(out + 1, packet, 187);
+            if (!crc_valid) {
+                out[1] |= 0x80;
+                h->error_cnt++;
+            }
+            out += 188;
+            produced += 188;
+            h->packet_cnt++;
+        }
+        if (df_remaining > 0) {
+            h->partial_ts_bytes = df_remaining;
+            memcpy(h->partial_pkt, p, df_remaining);
+        }
+    }
+    return produced;
+}

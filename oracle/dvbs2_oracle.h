@@ -75,6 +75,22 @@ void orc_demap_qpsk(const float* iq, int n_syms, float n0, int8_t* llr);
 /* soft demap + 3-column deinterleave; rate picks the column order */
 void orc_demap_8psk(const float* iq, int n_syms, float n0, int rate, int8_t* llr);
 
+/* ---- BB layer (lib/bbdescrambler_bb_impl.cc:51-82, lib/bbdeheader_bb_impl.cc:76-261) -------
+ * Pinned against the reference's two translation units compiled unmodified over a 60-line
+ * gr::block shim (oracle/ref_bb_harness.cc, oracle/shim/gnuradio/block.h) and against the
+ * reference's QA cases (python/dvbs2rx/qa_bbdeheader_bb.py) restated in tests/. */
+void orc_bb_prbs(uint8_t* seq, int nbytes);
+void orc_bb_descramble(const uint8_t* in, int frames, int kbch_bytes, uint8_t* out);
+uint8_t orc_crc8(const uint8_t* in, int size); /* 0 <=> check passes */
+typedef struct orc_bbdeheader orc_bbdeheader;
+orc_bbdeheader* orc_bbdeheader_create(int kbch);
+void orc_bbdeheader_destroy(orc_bbdeheader*);
+/* `frames` descrambled BBFRAMEs of kbch/8 bytes -> TS bytes in out (capacity frames * (kbch/8 + 188));
+ * state (sync, partial packet, counters) persists across calls.  Returns the bytes produced. */
+long orc_bbdeheader_work(orc_bbdeheader*, const uint8_t* in, int frames, uint8_t* out);
+/* packet, error, bbframe, bbframe_drop, bbframe_gap counts */
+void orc_bbdeheader_counters(const orc_bbdeheader*, uint64_t* out5);
+
 #ifdef __cplusplus
 }
 #endif

@@ -134,3 +134,29 @@ def test_sharding_under_gloo_world_size_2(built, tmp_path):
     assert a[0] == b[0]            # same table blob digest on both ranks
     assert (a[1], b[1]) == ("0:50", "50:100")  # contiguous shards of 100 frames
     assert a[2] == b[2] == "100"   # all-reduced frame counter
+
+
+def test_split_schedule_covers_every_table():
+    """Every conflict layer of the 57 tables has at most kMaxSharedLinks (12) shared links, so the split
+    form of the schedule exists for all of them; both forms of the blob build and validate."""
+    import os
+    from collections import Counter
+    worst = 0
+    for t in range(d.lib().dvbs2b200_num_tables()):
+        lay, grp, sh = d.table_circulants(t)
+        for layer in range(int(lay.max()) + 1):
+            c = Counter(grp[lay == layer].tolist())
+            worst = max(worst, sum(v for v in c.values() if v > 1))
+    assert worst == 12
+    old = os.environ.get("DVBS2B200_SPLIT")
+    try:
+        for mode in ("0", "1"):
+            os.environ["DVBS2B200_SPLIT"] = mode
+            for fs, rate in ((1, "C1_2"), (1, "C9_10"), (0, "C8_9"), (0, "C2_3")):
+                blob = d.build_tables(0, fs, d.RATE[rate])
+                assert blob.size > 1000
+    finally:
+        if old is None:
+            os.environ.pop("DVBS2B200_SPLIT", None)
+        else:
+            os.environ["DVBS2B200_SPLIT"] = old
