@@ -136,10 +136,10 @@ def test_sharding_under_gloo_world_size_2(built, tmp_path):
     assert a[2] == b[2] == "100"   # all-reduced frame counter
 
 
-def test_split_schedule_covers_every_table():
+def test_split_schedule_covers_every_table(built):
     """Every conflict layer of the 57 tables has at most kMaxSharedLinks (12) shared links, so the split
     form of the schedule exists for all of them; both forms of the blob build and validate."""
-    import os
+    import dvbs2rx_b200 as d
     from collections import Counter
     worst = 0
     for t in range(d.lib().dvbs2b200_num_tables()):
