@@ -83,6 +83,9 @@ struct dvbs2b200_code {
     uint64_t launches = 0;
     // staging for the host-pointer entry points
     DevBuf d_in, d_mid, d_out, d_post, d_i32a, d_i32b, d_n0, d_llr, d_sync, d_scratch, d_flag, d_prof;
+    // BB layer: descrambling sequence, deheader stream state, per-call scratch, TS output staging
+    DevBuf d_prbs, d_bbstate, d_bbrec, d_bbplan, d_ts;
+    bool bb_ready = false;
 };
 
 namespace {
@@ -375,6 +378,114 @@ int demap_dev(dvbs2b200_code* h, int constellation, const float* d_iq, int frame
     return DVBS2B200_OK;
 }
 
+// ---- BB layer ---------------------------------------------------------------------------------
+// lib/bbdescrambler_bb_impl.cc:51-65: PRBS 1 + x^14 + x^15, register loaded with 100101010000000
+void bb_prbs(std::vector<uint8_t>& seq, int nbytes)
+{
+    seq.assign((size_t)nbytes, 0);
+    int sr = 0x4A80;
+    for (int i = 0; i < nbytes * 8; i++) {
+        const int b = ((sr) ^ (sr >> 1)) & 1;
+        seq[i / 8] |= (uint8_t)(b << (7 - (i % 8)));
+        sr >>= 1;
+        if (b)
+            sr |= 0x4000;
+    }
+}
+
+int bb_ensure(dvbs2b200_code* h)
+{
+    if (h->bb_ready)
+        return DVBS2B200_OK;
+    const BlobHeader& hd = h->hdr;
+    if (hd.kbch <= 80 || hd.kbch % 8)
+        return fail(DVBS2B200_EUNSUPPORTED, "BBFRAME length must be a multiple of 8 bits");
+    int rc;
+    if ((rc = h->d_prbs.ensure((size_t)hd.kbch / 8)) || (rc = h->d_bbstate.ensure(sizeof(BbState))))
+        return rc;
+    std::vector<uint8_t> seq;
+    bb_prbs(seq, hd.kbch / 8);
+    CU(cudaMemcpy(h->d_prbs.p, seq.data(), seq.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemset(h->d_bbstate.p, 0, sizeof(BbState)));
+    h->bb_ready = true;
+    return DVBS2B200_OK;
+}
+
+size_t bb_ts_capacity(const BlobHeader& hd, int frames)
+{
+    // every BBFRAME yields at most (187 carried + its DATAFIELD) / 188 packets
+    return (size_t)frames * (((size_t)hd.kbch / 8 - 10 + 187) / 188) * 188;
+}
+
+int bb_descramble_dev(dvbs2b200_code* h, const uint8_t* d_in, int frames, uint8_t* d_out, cudaStream_t stream)
+{
+    if (frames < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames");
+    if (frames == 0)
+        return DVBS2B200_OK;
+    if (!d_in || !d_out)
+        return fail(DVBS2B200_EINVAL, "null buffer");
+    int rc = bb_ensure(h);
+    if (rc)
+        return rc;
+    cudaError_t e = bb_descramble_launch(d_in, d_out, (const uint8_t*)h->d_prbs.p, frames, h->hdr.kbch / 8, stream);
+    if (e != cudaSuccess)
+        return cuda_fail(e, "bb_descramble_launch");
+    h->launches += 1;
+    return DVBS2B200_OK;
+}
+
+int bb_deheader_dev(dvbs2b200_code* h, const uint8_t* d_bb, int frames, int scrambled, uint8_t* d_ts, size_t ts_cap,
+                    cudaStream_t stream)
+{
+    if (frames < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames");
+    int rc = bb_ensure(h);
+    if (rc)
+        return rc;
+    if (frames == 0) {
+        CU(cudaMemsetAsync(&((BbState*)h->d_bbstate.p)->produced, 0, sizeof(unsigned long long), stream));
+        return DVBS2B200_OK;
+    }
+    if (!d_bb || !d_ts)
+        return fail(DVBS2B200_EINVAL, "null buffer");
+    if ((rc = h->d_bbrec.ensure((size_t)frames * sizeof(uint32_t))) || (rc = h->d_bbplan.ensure((size_t)frames * sizeof(BbPlan))))
+        return rc;
+    BbLaunch p;
+    memset(&p, 0, sizeof(p));
+    p.bb = d_bb;
+    p.prbs = (const uint8_t*)h->d_prbs.p;
+    p.scrambled = scrambled ? 1 : 0;
+    p.frames = frames;
+    p.kbytes = h->hdr.kbch / 8;
+    p.rec = (uint32_t*)h->d_bbrec.p;
+    p.plan = (BbPlan*)h->d_bbplan.p;
+    p.state = (BbState*)h->d_bbstate.p;
+    p.ts = d_ts;
+    p.ts_cap = ts_cap;
+    cudaError_t e = bb_deheader_launch(p, stream);
+    if (e != cudaSuccess)
+        return cuda_fail(e, "bb_deheader_launch");
+    h->launches += 3;
+    return DVBS2B200_OK;
+}
+
+// after the kernels of a host-pointer call: read the byte count, copy the packets out
+int bb_fetch_ts(dvbs2b200_code* h, const uint8_t* d_ts, uint8_t* ts, size_t ts_cap, size_t* ts_bytes, cudaStream_t s)
+{
+    unsigned long long produced = 0;
+    CU(cudaMemcpyAsync(&produced, &((BbState*)h->d_bbstate.p)->produced, sizeof(produced), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (produced > ts_cap)
+        produced = ts_cap / 188 * 188;
+    if (produced)
+        CU(cudaMemcpyAsync(ts, d_ts, (size_t)produced, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (ts_bytes)
+        *ts_bytes = (size_t)produced;
+    return DVBS2B200_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -518,7 +629,8 @@ void dvbs2b200_code_destroy(dvbs2b200_code* h)
     DeviceGuard g(h->device);
     if (h->stream)
         cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : { &h->d_in, &h->d_mid, &h->d_out, &h->d_post, &h->d_i32a, &h->d_i32b, &h->d_n0, &h->d_llr, &h->d_sync, &h->d_scratch, &h->d_flag, &h->d_prof })
+    for (DevBuf* b : { &h->d_in, &h->d_mid, &h->d_out, &h->d_post, &h->d_i32a, &h->d_i32b, &h->d_n0, &h->d_llr, &h->d_sync, &h->d_scratch, &h->d_flag, &h->d_prof,
+                       &h->d_prbs, &h->d_bbstate, &h->d_bbrec, &h->d_bbplan, &h->d_ts })
         b->release();
     if (h->d_blob)
         cudaFree(h->d_blob);
@@ -878,6 +990,192 @@ int dvbs2b200_fec_decode(dvbs2b200_code* h, int constellation, const float* iq, 
 #undef CUP
     cleanup();
     return DVBS2B200_OK;
+}
+
+// ---- BB layer: descrambler, deheader, and the chain down to TS bytes --------------------------------
+int dvbs2b200_bb_descramble_dev(dvbs2b200_code* h, const uint8_t* d_in, int frames, uint8_t* d_out, void* stream)
+{
+    if (!h)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    DeviceGuard g(h->device);
+    return bb_descramble_dev(h, d_in, frames, d_out, (cudaStream_t)stream);
+}
+
+int dvbs2b200_bb_descramble(dvbs2b200_code* h, const uint8_t* in, int frames, uint8_t* out)
+{
+    if (!h)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    if (frames < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames");
+    if (frames == 0)
+        return DVBS2B200_OK;
+    if (!in || !out)
+        return fail(DVBS2B200_EINVAL, "null buffer");
+    DeviceGuard g(h->device);
+    const size_t bytes = (size_t)frames * (h->hdr.kbch / 8);
+    int rc;
+    if ((rc = h->d_mid.ensure(bytes)) || (rc = h->d_out.ensure(bytes)))
+        return rc;
+    cudaStream_t s = h->stream;
+    CU(cudaMemcpyAsync(h->d_mid.p, in, bytes, cudaMemcpyHostToDevice, s));
+    if ((rc = bb_descramble_dev(h, (const uint8_t*)h->d_mid.p, frames, (uint8_t*)h->d_out.p, s)))
+        return rc;
+    CU(cudaMemcpyAsync(out, h->d_out.p, bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return DVBS2B200_OK;
+}
+
+size_t dvbs2b200_bb_ts_capacity(const dvbs2b200_code* h, int frames)
+{
+    return (h && frames > 0) ? bb_ts_capacity(h->hdr, frames) : 0;
+}
+
+int dvbs2b200_bb_deheader_dev(dvbs2b200_code* h, const uint8_t* d_bbframes, int frames, int scrambled, uint8_t* d_ts,
+                              size_t ts_cap, void* stream)
+{
+    if (!h)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    DeviceGuard g(h->device);
+    return bb_deheader_dev(h, d_bbframes, frames, scrambled, d_ts, ts_cap, (cudaStream_t)stream);
+}
+
+int dvbs2b200_bb_deheader(dvbs2b200_code* h, const uint8_t* bbframes, int frames, int scrambled, uint8_t* ts, size_t ts_cap,
+                          size_t* ts_bytes)
+{
+    if (!h)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    if (frames < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames");
+    if (ts_bytes)
+        *ts_bytes = 0;
+    if (frames == 0)
+        return DVBS2B200_OK;
+    if (!bbframes || !ts)
+        return fail(DVBS2B200_EINVAL, "null buffer");
+    DeviceGuard g(h->device);
+    const size_t bytes = (size_t)frames * (h->hdr.kbch / 8);
+    const size_t cap = std::min(ts_cap, bb_ts_capacity(h->hdr, frames));
+    int rc;
+    if ((rc = h->d_mid.ensure(bytes)) || (rc = h->d_ts.ensure(cap + 256)))
+        return rc;
+    cudaStream_t s = h->stream;
+    CU(cudaMemcpyAsync(h->d_mid.p, bbframes, bytes, cudaMemcpyHostToDevice, s));
+    if ((rc = bb_deheader_dev(h, (const uint8_t*)h->d_mid.p, frames, scrambled, (uint8_t*)h->d_ts.p, cap, s)))
+        return rc;
+    return bb_fetch_ts(h, (const uint8_t*)h->d_ts.p, ts, cap, ts_bytes, s);
+}
+
+int dvbs2b200_bb_produced_dev(dvbs2b200_code* h, void* stream, size_t* ts_bytes)
+{
+    if (!h || !ts_bytes)
+        return fail(DVBS2B200_EINVAL, "null argument");
+    DeviceGuard g(h->device);
+    int rc = bb_ensure(h);
+    if (rc)
+        return rc;
+    unsigned long long produced = 0;
+    CU(cudaMemcpyAsync(&produced, &((BbState*)h->d_bbstate.p)->produced, sizeof(produced), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    *ts_bytes = (size_t)produced;
+    return DVBS2B200_OK;
+}
+
+int dvbs2b200_bb_reset(dvbs2b200_code* h)
+{
+    if (!h)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    DeviceGuard g(h->device);
+    int rc = bb_ensure(h);
+    if (rc)
+        return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemset(h->d_bbstate.p, 0, sizeof(BbState)));
+    return DVBS2B200_OK;
+}
+
+int dvbs2b200_bb_counters_get(dvbs2b200_code* h, dvbs2b200_bb_counters* c)
+{
+    if (!h || !c)
+        return fail(DVBS2B200_EINVAL, "null argument");
+    DeviceGuard g(h->device);
+    int rc = bb_ensure(h);
+    if (rc)
+        return rc;
+    BbState st;
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(&st, h->d_bbstate.p, sizeof(st), cudaMemcpyDeviceToHost));
+    c->packets = st.packet_cnt;
+    c->errors = st.error_cnt;
+    c->bbframes = st.bbframe_cnt;
+    c->dropped = st.bbframe_drop_cnt;
+    c->gaps = st.bbframe_gap_cnt;
+    return DVBS2B200_OK;
+}
+
+int dvbs2b200_fec_decode_ts_dev(dvbs2b200_code* h, int constellation, const float* d_iq, const float* d_n0, const int8_t* d_llr,
+                                int frames, int max_trials, int term_group, uint8_t* d_ts, size_t ts_cap, int32_t* d_trials_left,
+                                int32_t* d_corrections, void* stream)
+{
+    if (!h)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    if (frames < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames");
+    if (frames == 0)
+        return DVBS2B200_OK;
+    DeviceGuard g(h->device);
+    int rc;
+    if ((rc = h->d_out.ensure((size_t)frames * (h->hdr.kbch / 8))))
+        return rc;
+    if ((rc = dvbs2b200_fec_decode_dev(h, constellation, d_iq, d_n0, d_llr, frames, max_trials, term_group, (uint8_t*)h->d_out.p,
+                                       d_trials_left, d_corrections, stream)))
+        return rc;
+    return bb_deheader_dev(h, (const uint8_t*)h->d_out.p, frames, /*scrambled*/ 1, d_ts, ts_cap, (cudaStream_t)stream);
+}
+
+int dvbs2b200_fec_decode_ts(dvbs2b200_code* h, int constellation, const float* iq, const float* n0, const int8_t* llr, int frames,
+                            int max_trials, int term_group, uint8_t* ts, size_t ts_cap, size_t* ts_bytes, int32_t* trials_left,
+                            int32_t* corrections)
+{
+    if (!h)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    if (frames < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames");
+    if (ts_bytes)
+        *ts_bytes = 0;
+    if (frames == 0)
+        return DVBS2B200_OK;
+    if (!ts || (!iq && !llr))
+        return fail(DVBS2B200_EINVAL, "null buffer");
+    if (iq && !n0)
+        return fail(DVBS2B200_EINVAL, "n0 is null");
+    DeviceGuard g(h->device);
+    const BlobHeader& hd = h->hdr;
+    const int bits = iq ? bits_per_symbol(constellation) : 0;
+    if (iq && !bits)
+        return fail(DVBS2B200_EUNSUPPORTED, "Unsupported constellation");
+    const size_t in_bytes = (size_t)frames * (iq ? (size_t)(hd.N / bits) * 8 : (size_t)hd.N);
+    const size_t cap = std::min(ts_cap, bb_ts_capacity(hd, frames));
+    int rc;
+    if ((rc = h->d_in.ensure(in_bytes)) || (rc = h->d_ts.ensure(cap + 256)) || (rc = h->d_i32a.ensure((size_t)frames * 4)) ||
+        (rc = h->d_i32b.ensure((size_t)frames * 4)))
+        return rc;
+    if (iq && (rc = h->d_n0.ensure((size_t)frames * 4)))
+        return rc;
+    cudaStream_t s = h->stream;
+    CU(cudaMemcpyAsync(h->d_in.p, iq ? (const void*)iq : (const void*)llr, in_bytes, cudaMemcpyHostToDevice, s));
+    if (iq)
+        CU(cudaMemcpyAsync(h->d_n0.p, n0, (size_t)frames * 4, cudaMemcpyHostToDevice, s));
+    // the BBFRAMEs stay in device memory: only TS bytes (and the per-frame status words) travel back
+    rc = dvbs2b200_fec_decode_ts_dev(h, constellation, iq ? (const float*)h->d_in.p : nullptr, (const float*)h->d_n0.p,
+                                     iq ? nullptr : (const int8_t*)h->d_in.p, frames, max_trials, term_group, (uint8_t*)h->d_ts.p, cap,
+                                     (int32_t*)h->d_i32a.p, (int32_t*)h->d_i32b.p, s);
+    if (rc)
+        return rc;
+    if (trials_left)
+        CU(cudaMemcpyAsync(trials_left, h->d_i32a.p, (size_t)frames * 4, cudaMemcpyDeviceToHost, s));
+    if (corrections)
+        CU(cudaMemcpyAsync(corrections, h->d_i32b.p, (size_t)frames * 4, cudaMemcpyDeviceToHost, s));
+    return bb_fetch_ts(h, (const uint8_t*)h->d_ts.p, ts, cap, ts_bytes, s);
 }
 
 } // extern "C"

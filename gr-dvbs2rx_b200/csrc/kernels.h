@@ -76,6 +76,44 @@ struct DemapLaunch {
 };
 cudaError_t demap_launch(const DemapLaunch& p, cudaStream_t stream);
 
+// ---- BB layer: descrambler + deheader (bb_kernel.cu) --------------------------------------------------
+// Stream state of the deheader (lib/bbdeheader_bb_impl.h:40-53), in device memory, one per handle.
+struct BbState {
+    int synched;          // d_synched
+    unsigned int partial; // d_partial_ts_bytes
+    int carry_idx;        // which carry buffer holds d_partial_pkt after the call
+    int read_idx;         // which one held it before (read by the call's first completed packet)
+    int carry_src_frame;  // frame of this call whose tail becomes the new partial packet, or -1
+    unsigned int carry_src_off, carry_len;
+    unsigned int pad;
+    unsigned long long packet_cnt, error_cnt, bbframe_cnt, bbframe_drop_cnt, bbframe_gap_cnt;
+    unsigned long long produced; // TS bytes written by the last call
+    uint8_t carry[2][192];
+};
+// Per BBFRAME: what the frame contributes to the output.
+struct BbPlan {
+    uint32_t out_pkt;  // index of its first packet in the output of this call
+    uint32_t n_pkts;
+    uint32_t p_in;     // bytes of a carried partial packet in front of its first packet
+    uint32_t skip;     // DATAFIELD bytes skipped on re-synchronisation (syncd/8 + 1)
+    int32_t src_frame; // where those p_in bytes are: a frame of this call, or -1 = the state's carry buffer
+    uint32_t src_off;  // offset into that frame's DATAFIELD
+};
+struct BbLaunch {
+    const uint8_t* bb;   // [frames][kbytes] BBFRAMEs (BCH output)
+    const uint8_t* prbs; // [kbytes] descrambling sequence
+    int scrambled;       // 1: bb is still scrambled (descramble on the fly), 0: already descrambled
+    int frames, kbytes;
+    uint32_t* rec;       // [frames] scratch
+    BbPlan* plan;        // [frames] scratch
+    BbState* state;
+    uint8_t* ts;         // output, capacity ts_cap bytes
+    unsigned long long ts_cap;
+};
+cudaError_t bb_descramble_launch(const uint8_t* in, uint8_t* out, const uint8_t* prbs, int frames, int kbytes, cudaStream_t stream);
+// three launches: header records, state scan, packet extraction
+cudaError_t bb_deheader_launch(const BbLaunch& p, cudaStream_t stream);
+
 // one-thread kernel that publishes `value` at *flag (stream-ordered after the copies before it)
 cudaError_t flag_launch(unsigned int* flag, unsigned int value, cudaStream_t stream);
 

@@ -75,6 +75,17 @@ _SIGS = {
     "dvbs2b200_demap_dev": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, _P]),
     "dvbs2b200_fec_decode": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "dvbs2b200_fec_decode_dev": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "dvbs2b200_bb_descramble": (C.c_int, [_P, _P, C.c_int, _P]),
+    "dvbs2b200_bb_descramble_dev": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "dvbs2b200_bb_ts_capacity": (C.c_size_t, [_P, C.c_int]),
+    "dvbs2b200_bb_deheader": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "dvbs2b200_bb_deheader_dev": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_size_t, _P]),
+    "dvbs2b200_bb_produced_dev": (C.c_int, [_P, _P, C.POINTER(C.c_size_t)]),
+    "dvbs2b200_bb_reset": (C.c_int, [_P]),
+    "dvbs2b200_bb_counters_get": (C.c_int, [_P, _P]),
+    "dvbs2b200_fec_decode_ts": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_size_t,
+                                          C.POINTER(C.c_size_t), _P, _P]),
+    "dvbs2b200_fec_decode_ts_dev": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(sorted(_SIGS))
 
@@ -243,6 +254,71 @@ class Code:
         _check(lib().dvbs2b200_fec_decode(self._h, constellation, _ptr(iq), _ptr(n0), _ptr(llr), F, max_trials,
                                           term_group, msg.ctypes.data, trials.ctypes.data, corr.ctypes.data))
         return msg, trials, corr
+
+    # ---- BB layer: BBFRAMEs -> TS packets (bbdescrambler_bb / bbdeheader_bb) ---------------------
+    def bb_descramble(self, bbframes):
+        bb = _np(bbframes, np.uint8).reshape(-1, self.kbch // 8)
+        out = np.empty_like(bb)
+        _check(lib().dvbs2b200_bb_descramble(self._h, bb.ctypes.data, bb.shape[0], out.ctypes.data))
+        return out
+
+    def bb_ts_capacity(self, frames):
+        return int(lib().dvbs2b200_bb_ts_capacity(self._h, frames))
+
+    def bb_deheader(self, bbframes, scrambled=False):
+        """Stateful, like the reference block: returns the TS bytes this call produced."""
+        bb = _np(bbframes, np.uint8).reshape(-1, self.kbch // 8)
+        F = bb.shape[0]
+        ts = np.empty(max(self.bb_ts_capacity(F), 188), dtype=np.uint8)
+        n = C.c_size_t()
+        _check(lib().dvbs2b200_bb_deheader(self._h, bb.ctypes.data, F, 1 if scrambled else 0, ts.ctypes.data, ts.size, C.byref(n)))
+        return ts[:n.value].copy()
+
+    def bb_reset(self):
+        _check(lib().dvbs2b200_bb_reset(self._h))
+
+    def bb_counters(self):
+        c = (C.c_uint64 * 5)()
+        _check(lib().dvbs2b200_bb_counters_get(self._h, c))
+        return dict(zip(("packets", "errors", "bbframes", "dropped", "gaps"), [int(v) for v in c]))
+
+    def fec_decode_ts(self, llr=None, iq=None, n0=None, constellation=0, max_trials=25, term_group=TERM_PER_FRAME):
+        """Soft input -> TS packets with every intermediate in device memory."""
+        if iq is not None:
+            bits = bits_per_symbol(constellation)
+            iq = _np(iq, np.float32).reshape(-1, self.N // bits, 2)
+            F = iq.shape[0]
+            n0 = _np(np.broadcast_to(np.asarray(n0, dtype=np.float32), (F,)), np.float32)
+        else:
+            llr = _np(llr, np.int8).reshape(-1, self.N)
+            F = llr.shape[0]
+        ts = np.empty(max(self.bb_ts_capacity(F), 188), dtype=np.uint8)
+        n = C.c_size_t()
+        trials = np.empty(F, dtype=np.int32)
+        corr = np.empty(F, dtype=np.int32)
+        _check(lib().dvbs2b200_fec_decode_ts(self._h, constellation, _ptr(iq), _ptr(n0), _ptr(llr), F, max_trials, term_group,
+                                             ts.ctypes.data, ts.size, C.byref(n), trials.ctypes.data, corr.ctypes.data))
+        return ts[:n.value].copy(), trials, corr
+
+    def fec_decode_ts_ptr(self, constellation, iq_ptr, n0_ptr, llr_ptr, frames, max_trials, term_group, ts_ptr, ts_cap,
+                          trials_ptr, corr_ptr):
+        n = C.c_size_t()
+        _check(lib().dvbs2b200_fec_decode_ts(self._h, constellation, iq_ptr, n0_ptr, llr_ptr, frames, max_trials, term_group,
+                                             ts_ptr, ts_cap, C.byref(n), trials_ptr, corr_ptr))
+        return n.value
+
+    def bb_deheader_dev(self, d_bb, frames, scrambled, d_ts, ts_cap, stream):
+        _check(lib().dvbs2b200_bb_deheader_dev(self._h, d_bb, frames, scrambled, d_ts, ts_cap, stream))
+
+    def bb_produced_dev(self, stream):
+        n = C.c_size_t()
+        _check(lib().dvbs2b200_bb_produced_dev(self._h, stream, C.byref(n)))
+        return n.value
+
+    def fec_decode_ts_dev(self, constellation, d_iq, d_n0, d_llr, frames, max_trials, term_group, d_ts, ts_cap, d_trials,
+                          d_corr, stream):
+        _check(lib().dvbs2b200_fec_decode_ts_dev(self._h, constellation, d_iq, d_n0, d_llr, frames, max_trials, term_group,
+                                                 d_ts, ts_cap, d_trials, d_corr, stream))
 
     # ---- raw-pointer entry points (device or pinned host addresses as ints) ----------------------
     def ldpc_decode_ptr(self, llr_ptr, frames, max_trials, term_group, output_mode, hard_ptr, post_ptr, trials_ptr):

@@ -148,6 +148,77 @@ int bch_decoder_bb::general_work(int noutput_items, gr_vector_int& /*ninput_item
     return noutput_items;
 }
 
+// ---- bbdescrambler_bb -----------------------------------------------------------------------------
+bbdescrambler_bb::sptr bbdescrambler_bb::make(dvb_standard_t standard, dvb_framesize_t framesize, dvb_code_rate_t rate)
+{
+    sptr b(new bbdescrambler_bb());
+    b->d_code = create_code(standard, framesize, rate);
+    dvbs2b200_code_info info;
+    dvbs2b200_code_info_get(b->d_code, &info);
+    b->kbch_bytes = info.kbch / 8; // lib/bbdescrambler_bb_impl.cc:41-44
+    return b;
+}
+
+bbdescrambler_bb::~bbdescrambler_bb() { dvbs2b200_code_destroy(d_code); }
+
+int bbdescrambler_bb::work(int noutput_items, gr_vector_const_void_star& input_items, gr_vector_void_star& output_items)
+{
+    // lib/bbdescrambler_bb_impl.cc:67-82; noutput_items is a multiple of kbch_bytes (set_output_multiple)
+    int rc = dvbs2b200_bb_descramble(d_code, (const unsigned char*)input_items[0], noutput_items / (int)kbch_bytes,
+                                     (unsigned char*)output_items[0]);
+    if (rc != DVBS2B200_OK)
+        throw std::runtime_error(std::string("dvbs2b200_bb_descramble: ") + dvbs2b200_last_error());
+    return noutput_items;
+}
+
+// ---- bbdeheader_bb --------------------------------------------------------------------------------
+bbdeheader_bb::sptr bbdeheader_bb::make(dvb_standard_t standard, dvb_framesize_t framesize, dvb_code_rate_t rate,
+                                        int /*debug_level*/)
+{
+    sptr b(new bbdeheader_bb());
+    b->d_code = create_code(standard, framesize, rate);
+    dvbs2b200_code_info info;
+    dvbs2b200_code_info_get(b->d_code, &info);
+    b->d_kbch_bytes = info.kbch / 8;   // lib/bbdeheader_bb_impl.cc:57-61
+    b->d_max_dfl = info.kbch - 80;
+    return b;
+}
+
+bbdeheader_bb::~bbdeheader_bb() { dvbs2b200_code_destroy(d_code); }
+
+void bbdeheader_bb::forecast(int noutput_items, gr_vector_int& ninput_items_required)
+{
+    // lib/bbdeheader_bb_impl.cc:69-74
+    unsigned int n_bbframes = (unsigned int)std::ceil(static_cast<double>(noutput_items * 8) / d_max_dfl);
+    ninput_items_required[0] = n_bbframes * d_kbch_bytes;
+}
+
+int bbdeheader_bb::general_work(int noutput_items, gr_vector_int& ninput_items, gr_vector_const_void_star& input_items,
+                                gr_vector_void_star& output_items)
+{
+    // lib/bbdeheader_bb_impl.cc:154-160: as many whole BBFRAMEs as are available and fit
+    const unsigned int in_bbframes = ninput_items[0] / d_kbch_bytes;
+    const unsigned int out_bbframes = (unsigned int)std::ceil(static_cast<double>(noutput_items * 8) / d_max_dfl);
+    const unsigned int n_bbframes = std::min(in_bbframes, out_bbframes);
+    size_t produced = 0;
+    // like the reference, up to one packet more than noutput_items can come out (a carried partial packet)
+    int rc = dvbs2b200_bb_deheader(d_code, (const unsigned char*)input_items[0], (int)n_bbframes, d_scrambled ? 1 : 0,
+                                   (unsigned char*)output_items[0], dvbs2b200_bb_ts_capacity(d_code, (int)n_bbframes), &produced);
+    if (rc != DVBS2B200_OK)
+        throw std::runtime_error(std::string("dvbs2b200_bb_deheader: ") + dvbs2b200_last_error());
+    d_consumed = (int)(n_bbframes * d_kbch_bytes);
+    return (int)produced;
+}
+
+uint64_t bbdeheader_bb::counters(int which)
+{
+    dvbs2b200_bb_counters c;
+    if (dvbs2b200_bb_counters_get(d_code, &c) != DVBS2B200_OK)
+        throw std::runtime_error(std::string("dvbs2b200_bb_counters_get: ") + dvbs2b200_last_error());
+    const uint64_t v[5] = { c.packets, c.errors, c.bbframes, c.dropped, c.gaps };
+    return v[which];
+}
+
 // ---- xfecframe_demapper_cb ------------------------------------------------------------------------
 xfecframe_demapper_cb::sptr xfecframe_demapper_cb::make(dvb_framesize_t framesize, dvb_code_rate_t rate,
                                                         dvb_constellation_t constellation)
@@ -440,6 +511,65 @@ int blk_bch_work(void* h, int noutput_items, const unsigned char* in, unsigned c
 }
 uint64_t blk_bch_frame_count(void* h) { return (*(bch_decoder_bb::sptr*)h)->get_frame_count(); }
 uint64_t blk_bch_error_count(void* h) { return (*(bch_decoder_bb::sptr*)h)->get_error_count(); }
+
+void* blk_bbdescrambler_make(int standard, int framesize, int rate)
+{
+    try {
+        return new bbdescrambler_bb::sptr(bbdescrambler_bb::make((dvb_standard_t)standard, (dvb_framesize_t)framesize, (dvb_code_rate_t)rate));
+    } catch (...) {
+        return nullptr;
+    }
+}
+void blk_bbdescrambler_free(void* h) { delete (bbdescrambler_bb::sptr*)h; }
+int blk_bbdescrambler_work(void* h, int noutput_items, const unsigned char* in, unsigned char* out)
+{
+    gr_vector_const_void_star ins(1, in);
+    gr_vector_void_star outs(1, out);
+    try {
+        return (*(bbdescrambler_bb::sptr*)h)->work(noutput_items, ins, outs);
+    } catch (...) {
+        return -1000;
+    }
+}
+
+void* blk_bbdeheader_make(int standard, int framesize, int rate)
+{
+    try {
+        return new bbdeheader_bb::sptr(bbdeheader_bb::make((dvb_standard_t)standard, (dvb_framesize_t)framesize, (dvb_code_rate_t)rate));
+    } catch (...) {
+        return nullptr;
+    }
+}
+void blk_bbdeheader_free(void* h) { delete (bbdeheader_bb::sptr*)h; }
+int blk_bbdeheader_work(void* h, int noutput_items, int ninput_items, const unsigned char* in, unsigned char* out, int* consumed)
+{
+    auto& b = *(bbdeheader_bb::sptr*)h;
+    gr_vector_int ninput(1, ninput_items);
+    gr_vector_const_void_star ins(1, in);
+    gr_vector_void_star outs(1, out);
+    try {
+        int r = b->general_work(noutput_items, ninput, ins, outs);
+        *consumed = b->consumed();
+        return r;
+    } catch (...) {
+        return -1000;
+    }
+}
+int blk_bbdeheader_forecast(void* h, int noutput_items)
+{
+    gr_vector_int req(1, 0);
+    (*(bbdeheader_bb::sptr*)h)->forecast(noutput_items, req);
+    return req[0];
+}
+void blk_bbdeheader_counters(void* h, uint64_t* out5)
+{
+    auto& b = *(bbdeheader_bb::sptr*)h;
+    out5[0] = b->get_packet_count();
+    out5[1] = b->get_error_count();
+    out5[2] = b->get_bbframe_count();
+    out5[3] = b->get_bbframe_drop_count();
+    out5[4] = b->get_bbframe_gap_count();
+}
 
 void* blk_demap_make(int framesize, int rate, int constellation, char* err, int errcap)
 {

@@ -9,6 +9,8 @@
 //   ldpc_decoder_bb        <- include/gnuradio/dvbs2rx/ldpc_decoder_bb.h:38-51, lib/ldpc_decoder_bb_impl.{h,cc}
 //   bch_decoder_bb         <- include/gnuradio/dvbs2rx/bch_decoder_bb.h:39-55,  lib/bch_decoder_bb_impl.{h,cc}
 //   xfecframe_demapper_cb  <- include/gnuradio/dvbs2rx/xfecframe_demapper_cb.h:36-44, lib/xfecframe_demapper_cb_impl.{h,cc}
+//   bbdescrambler_bb       <- include/gnuradio/dvbs2rx/bbdescrambler_bb.h, lib/bbdescrambler_bb_impl.{h,cc}
+//   bbdeheader_bb          <- include/gnuradio/dvbs2rx/bbdeheader_bb.h,    lib/bbdeheader_bb_impl.{h,cc}
 // and ldpc_cuda::ldpc_dec_init / ldpc_dec_decode, the pair that slots in beside the reference's ISA
 // namespaces (lib/ldpc_decoder_bb_impl.cc:34-52) behind `int (*decode)(void*, int8_t*, int)`.
 #pragma once
@@ -144,6 +146,52 @@ private:
     std::array<uint64_t, kPool> d_saved;
     size_t d_idx = 0;
     std::vector<float> d_n0_per_frame;
+};
+
+// bbdescrambler_bb <- include/gnuradio/dvbs2rx/bbdescrambler_bb.h, lib/bbdescrambler_bb_impl.{h,cc} (a gr::sync_block)
+class bbdescrambler_bb
+{
+public:
+    typedef std::shared_ptr<bbdescrambler_bb> sptr;
+    static sptr make(dvb_standard_t standard, dvb_framesize_t framesize, dvb_code_rate_t rate);
+    ~bbdescrambler_bb();
+    int work(int noutput_items, gr_vector_const_void_star& input_items, gr_vector_void_star& output_items);
+    int output_multiple() const { return (int)kbch_bytes; }
+
+private:
+    bbdescrambler_bb() {}
+    dvbs2b200_code* d_code = nullptr;
+    unsigned int kbch_bytes;
+};
+
+// bbdeheader_bb <- include/gnuradio/dvbs2rx/bbdeheader_bb.h:27-72, lib/bbdeheader_bb_impl.{h,cc}.
+// The stream state (synchronised?, partial TS packet) lives in the handle's device memory.
+class bbdeheader_bb
+{
+public:
+    typedef std::shared_ptr<bbdeheader_bb> sptr;
+    static sptr make(dvb_standard_t standard, dvb_framesize_t framesize, dvb_code_rate_t rate, int debug_level = 0);
+    ~bbdeheader_bb();
+    void forecast(int noutput_items, gr_vector_int& ninput_items_required);
+    int general_work(int noutput_items, gr_vector_int& ninput_items, gr_vector_const_void_star& input_items,
+                     gr_vector_void_star& output_items);
+    uint64_t get_packet_count() { return counters(0); }
+    uint64_t get_error_count() { return counters(1); }
+    uint64_t get_bbframe_count() { return counters(2); }
+    uint64_t get_bbframe_drop_count() { return counters(3); }
+    uint64_t get_bbframe_gap_count() { return counters(4); }
+    int output_multiple() const { return (int)(d_max_dfl / 8); }
+    int consumed() const { return d_consumed; }
+    // input is BCH output that has not been through bbdescrambler_bb: descramble on the fly (one block less)
+    void set_scrambled_input(bool on) { d_scrambled = on; }
+
+private:
+    bbdeheader_bb() {}
+    uint64_t counters(int which);
+    dvbs2b200_code* d_code = nullptr;
+    unsigned int d_kbch_bytes, d_max_dfl;
+    int d_consumed = 0;
+    bool d_scrambled = false;
 };
 
 } // namespace dvbs2rx

@@ -154,6 +154,52 @@ int dvbs2b200_fec_decode_dev(dvbs2b200_code* h, int constellation, const float* 
                              int term_group, uint8_t* d_msg, int32_t* d_trials_left,
                              int32_t* d_corrections, void* stream);
 
+/* ---- BB layer: descrambler + deheader, BBFRAMEs -> MPEG-TS bytes ------------------------------ */
+/* dvbs2b200_bb_descramble  <- bbdescrambler_bb_impl::work             lib/bbdescrambler_bb_impl.cc:67-82
+ * dvbs2b200_bb_deheader    <- bbdeheader_bb_impl::general_work        lib/bbdeheader_bb_impl.cc:144-261
+ *                             (+ parse_bbheader / check_crc8          lib/bbdeheader_bb_impl.cc:76-142)
+ * dvbs2b200_bb_counters_get<- get_packet_count ... get_bbframe_gap_count  lib/bbdeheader_bb_impl.h:89-93
+ * dvbs2b200_fec_decode_ts  <- ldpc_decoder_bb -> bch_decoder_bb -> bbdescrambler_bb -> bbdeheader_bb chained
+ *
+ * in/out [frames][kbch/8] BBFRAMEs.  The deheader is a stream: whether it is synchronised and the bytes of
+ * a TS packet cut by a BBFRAME boundary carry over from call to call in the handle (device memory), exactly
+ * the reference block's members; dvbs2b200_bb_reset() puts it back to the just-constructed state.
+ * ts receives whole 188-byte packets (sync byte restored, transport-error indicator set on a CRC-8 failure);
+ * dvbs2b200_bb_ts_capacity(frames) bytes always suffice.  scrambled != 0: the input is BCH output and is
+ * descrambled on the fly (bbdescrambler_bb fused in); 0: already descrambled, as the reference block expects.
+ * One deviation: where the reference's unsigned arithmetic wraps and reads past the BBFRAME (re-synchronising
+ * on a header with syncd == dfl, lib/bbdeheader_bb_impl.cc:203-209), that frame yields no packet here. */
+typedef struct {
+    uint64_t packets;  /* get_packet_count()       */
+    uint64_t errors;   /* get_error_count(): packets whose CRC-8 failed */
+    uint64_t bbframes; /* get_bbframe_count()      */
+    uint64_t dropped;  /* get_bbframe_drop_count() */
+    uint64_t gaps;     /* get_bbframe_gap_count()  */
+} dvbs2b200_bb_counters;
+
+int dvbs2b200_bb_descramble(dvbs2b200_code* h, const uint8_t* in, int frames, uint8_t* out);
+int dvbs2b200_bb_descramble_dev(dvbs2b200_code* h, const uint8_t* d_in, int frames, uint8_t* d_out, void* stream);
+size_t dvbs2b200_bb_ts_capacity(const dvbs2b200_code* h, int frames);
+int dvbs2b200_bb_deheader(dvbs2b200_code* h, const uint8_t* bbframes, int frames, int scrambled, uint8_t* ts,
+                          size_t ts_cap, size_t* ts_bytes);
+/* device variant: the byte count of the call is read back with dvbs2b200_bb_produced_dev after the stream
+ * has been synchronised (it lives in the handle's device state). */
+int dvbs2b200_bb_deheader_dev(dvbs2b200_code* h, const uint8_t* d_bbframes, int frames, int scrambled,
+                              uint8_t* d_ts, size_t ts_cap, void* stream);
+int dvbs2b200_bb_produced_dev(dvbs2b200_code* h, void* stream, size_t* ts_bytes);
+int dvbs2b200_bb_reset(dvbs2b200_code* h);
+int dvbs2b200_bb_counters_get(dvbs2b200_code* h, dvbs2b200_bb_counters* c);
+
+/* [demap ->] LDPC -> BCH -> descrambler -> deheader with every intermediate in device memory: soft input
+ * in, TS packets out.  Arguments as dvbs2b200_fec_decode; only TS bytes and the status words travel back. */
+int dvbs2b200_fec_decode_ts(dvbs2b200_code* h, int constellation, const float* iq, const float* n0,
+                            const int8_t* llr, int frames, int max_trials, int term_group, uint8_t* ts,
+                            size_t ts_cap, size_t* ts_bytes, int32_t* trials_left, int32_t* corrections);
+int dvbs2b200_fec_decode_ts_dev(dvbs2b200_code* h, int constellation, const float* d_iq, const float* d_n0,
+                                const int8_t* d_llr, int frames, int max_trials, int term_group,
+                                uint8_t* d_ts, size_t ts_cap, int32_t* d_trials_left,
+                                int32_t* d_corrections, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

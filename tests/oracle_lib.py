@@ -17,6 +17,31 @@ def _p(a):
     return None if a is None else a.ctypes.data
 
 
+class OracleDeheader:
+    """Stateful restatement of bbdeheader_bb (oracle/dvbs2_oracle.c)."""
+
+    def __init__(self, l, kbch):
+        self.l, self.kbch = l, kbch
+        self.h = l.orc_bbdeheader_create(kbch)
+
+    def work(self, bbframes):
+        bb = np.ascontiguousarray(bbframes, dtype=np.uint8).reshape(-1, self.kbch // 8)
+        out = np.zeros(bb.shape[0] * (self.kbch // 8 + 188) + 188, dtype=np.uint8)
+        n = self.l.orc_bbdeheader_work(self.h, bb.ctypes.data, bb.shape[0], out.ctypes.data)
+        return out[:n].copy()
+
+    def counters(self):
+        c = (C.c_uint64 * 5)()
+        self.l.orc_bbdeheader_counters(self.h, c)
+        return dict(zip(("packets", "errors", "bbframes", "dropped", "gaps"), [int(v) for v in c]))
+
+    def __del__(self):
+        try:
+            self.l.orc_bbdeheader_destroy(self.h)
+        except Exception:
+            pass
+
+
 class Oracle:
     def __init__(self):
         l = self.l = C.CDLL(ORACLE_PATH)
@@ -46,8 +71,37 @@ class Oracle:
         l.orc_bch_err_loc_numbers.argtypes = [_P, _P, C.c_int, _P]
         l.orc_demap_qpsk.argtypes = [_P, C.c_int, C.c_float, _P]
         l.orc_demap_8psk.argtypes = [_P, C.c_int, C.c_float, C.c_int, _P]
+        l.orc_bb_prbs.argtypes = [_P, C.c_int]
+        l.orc_bb_descramble.argtypes = [_P, C.c_int, C.c_int, _P]
+        l.orc_crc8.argtypes = [_P, C.c_int]
+        l.orc_crc8.restype = C.c_uint8
+        l.orc_bbdeheader_create.restype = _P
+        l.orc_bbdeheader_create.argtypes = [C.c_int]
+        l.orc_bbdeheader_destroy.argtypes = [_P]
+        l.orc_bbdeheader_work.argtypes = [_P, _P, C.c_int, _P]
+        l.orc_bbdeheader_work.restype = C.c_long
+        l.orc_bbdeheader_counters.argtypes = [_P, _P]
         self._ldpc = {}
         self._bch = {}
+
+    # ---- BB layer ----
+    def bb_prbs(self, nbytes):
+        seq = np.zeros(nbytes, dtype=np.uint8)
+        self.l.orc_bb_prbs(seq.ctypes.data, nbytes)
+        return seq
+
+    def bb_descramble(self, bbframes, kbch):
+        bb = np.ascontiguousarray(bbframes, dtype=np.uint8).reshape(-1, kbch // 8)
+        out = np.empty_like(bb)
+        self.l.orc_bb_descramble(bb.ctypes.data, bb.shape[0], kbch // 8, out.ctypes.data)
+        return out
+
+    def crc8(self, data):
+        a = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))
+        return int(self.l.orc_crc8(a.ctypes.data, a.size))
+
+    def bbdeheader(self, kbch):
+        return OracleDeheader(self.l, kbch)
 
     def lookup(self, standard, framesize, rate):
         k, n, t = C.c_int(), C.c_int(), C.c_int()
@@ -147,6 +201,32 @@ class Oracle:
         return out
 
 
+class RefDeheader:
+    """bbdeheader_bb_impl of the reference, compiled unmodified (oracle/ref_bb_harness.cc)."""
+
+    def __init__(self, l, standard, framesize, rate, kbch):
+        self.l, self.kbch = l, kbch
+        self.h = l.ref_bbdeheader_create(standard, framesize, rate)
+        assert self.h
+
+    def work(self, bbframes):
+        bb = np.ascontiguousarray(bbframes, dtype=np.uint8).reshape(-1, self.kbch // 8)
+        out = np.zeros(bb.shape[0] * (self.kbch // 8 + 188) + 188, dtype=np.uint8)
+        n = self.l.ref_bbdeheader_work(self.h, bb.ctypes.data, bb.size, out.ctypes.data, out.size - 188)
+        return out[:n].copy()
+
+    def counters(self):
+        c = (C.c_uint64 * 5)()
+        self.l.ref_bbdeheader_counters(self.h, c)
+        return dict(zip(("packets", "errors", "bbframes", "dropped", "gaps"), [int(v) for v in c]))
+
+    def __del__(self):
+        try:
+            self.l.ref_bbdeheader_destroy(self.h)
+        except Exception:
+            pass
+
+
 class Ref:
     """The compiled, unmodified reference (oracle/_ref)."""
 
@@ -175,7 +255,24 @@ class Ref:
         l.ref_bch_decode_mt.restype = C.c_double
         l.ref_demap_8psk.argtypes = [_P, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, _P]
         l.ref_demap_qpsk_psk4.argtypes = [_P, C.c_int, C.c_float, _P]
+        l.ref_bb_descramble.argtypes = [C.c_int, C.c_int, C.c_int, _P, C.c_int, _P]
+        l.ref_bbdeheader_create.restype = _P
+        l.ref_bbdeheader_create.argtypes = [C.c_int, C.c_int, C.c_int]
+        l.ref_bbdeheader_destroy.argtypes = [_P]
+        l.ref_bbdeheader_work.argtypes = [_P, _P, C.c_int, _P, C.c_int]
+        l.ref_bbdeheader_counters.argtypes = [_P, _P]
         self._init = {}
+
+    # ---- BB layer: the reference's own blocks over the gr::block shim ----
+    def bb_descramble(self, standard, framesize, rate, bbframes):
+        bb = np.ascontiguousarray(bbframes, dtype=np.uint8).ravel()
+        out = np.empty_like(bb)
+        n = self.l.ref_bb_descramble(standard, framesize, rate, bb.ctypes.data, bb.size, out.ctypes.data)
+        assert n == bb.size
+        return out
+
+    def bbdeheader(self, standard, framesize, rate, kbch):
+        return RefDeheader(self.l, standard, framesize, rate, kbch)
 
     def ldpc_decode(self, table_name, llr, trials=25, isa="avx2"):
         """Batches of the ISA's SIMD width through ldpc_<isa>::ldpc_dec_decode, in place."""

@@ -31,6 +31,16 @@ def blk(gpu):
     l.blk_bch_frame_count.restype = C.c_uint64
     l.blk_bch_error_count.argtypes = [_P]
     l.blk_bch_error_count.restype = C.c_uint64
+    l.blk_bbdescrambler_make.restype = _P
+    l.blk_bbdescrambler_make.argtypes = [C.c_int] * 3
+    l.blk_bbdescrambler_free.argtypes = [_P]
+    l.blk_bbdescrambler_work.argtypes = [_P, C.c_int, _P, _P]
+    l.blk_bbdeheader_make.restype = _P
+    l.blk_bbdeheader_make.argtypes = [C.c_int] * 3
+    l.blk_bbdeheader_free.argtypes = [_P]
+    l.blk_bbdeheader_work.argtypes = [_P, C.c_int, C.c_int, _P, _P, C.POINTER(C.c_int)]
+    l.blk_bbdeheader_forecast.argtypes = [_P, C.c_int]
+    l.blk_bbdeheader_counters.argtypes = [_P, _P]
     l.blk_demap_make.restype = _P
     l.blk_demap_make.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
     l.blk_demap_free.argtypes = [_P]
@@ -128,3 +138,40 @@ def test_demapper_block(blk, gpu, oracle):
     blk.blk_demap_llr_pdu(h, 32, 0, pdu.ctypes.data, pdu.size)
     assert abs(blk.blk_demap_snr(h) - 6.0) < 0.1
     blk.blk_demap_free(h)
+
+
+def test_bb_blocks_against_oracle(blk, gpu, oracle):
+    """bbdescrambler_bb::work and bbdeheader_bb::general_work / forecast / counters, driven the way the GNU
+    Radio scheduler drives the reference blocks (python/dvbs2rx/qa_bbdeheader_bb.py: QPSK 1/4 normal)."""
+    d = gpu
+    from dvbs2rx_b200 import bbframes as bbf
+    kbch, kb = 16008, 16008 // 8
+    rng = np.random.default_rng(12)
+    n = 10
+    up = bbf.ts_packets((n * (kb - 10) + 187) // 188 + 1, rng)
+    bb = bbf.bbframe_stream(kbch, n, up)
+    bb[4, 9] ^= 0xFF  # one BBHEADER fails its CRC
+    scr = bbf.scramble(bb)
+    hs = blk.blk_bbdescrambler_make(0, 1, d.C1_4)
+    out = np.zeros_like(scr)
+    assert blk.blk_bbdescrambler_work(hs, scr.size, scr.ctypes.data, out.ctypes.data) == scr.size
+    assert np.array_equal(out, bb) and np.array_equal(out, oracle.bb_descramble(scr, kbch))
+    blk.blk_bbdescrambler_free(hs)
+    hd = blk.blk_bbdeheader_make(0, 1, d.C1_4)
+    max_dfl_bytes = (kbch - 80) // 8
+    assert blk.blk_bbdeheader_forecast(hd, 2 * max_dfl_bytes) == 2 * kb  # lib/bbdeheader_bb_impl.cc:69-74
+    o = oracle.bbdeheader(kbch)
+    got, consumed = [], C.c_int()
+    for f0 in range(0, n, 2):  # the scheduler hands over two BBFRAMEs' worth of output space at a time
+        part = np.ascontiguousarray(out[f0:f0 + 2])
+        ts = np.zeros(2 * max_dfl_bytes + 188, np.uint8)
+        r = blk.blk_bbdeheader_work(hd, 2 * max_dfl_bytes, part.size, part.ctypes.data, ts.ctypes.data, C.byref(consumed))
+        assert consumed.value == 2 * kb
+        want = o.work(part)
+        assert r == want.size and np.array_equal(ts[:r], want)
+        got.append(ts[:r].copy())
+    c = (C.c_uint64 * 5)()
+    blk.blk_bbdeheader_counters(hd, c)
+    assert dict(zip(("packets", "errors", "bbframes", "dropped", "gaps"), [int(v) for v in c])) == o.counters()
+    assert o.counters()["dropped"] == 1
+    blk.blk_bbdeheader_free(hd)

@@ -137,7 +137,34 @@ def gen_demap():
                        cases=cases), f, indent=1)
 
 
+def gen_bb():
+    """BB deheader: the reference's bbdeheader_bb_impl.cc (compiled unmodified over the gr::block shim) on
+    the streams of tests/bb_cases.py."""
+    import bb_cases
+    rate_of = {16008: (1, "C1_4"), 3072: (0, "C1_4"), 58192: (1, "C9_10")}
+    cases = {}
+    for name, kbch, calls in bb_cases.make_cases():
+        fs, rate = rate_of[kbch]
+        r = ref.bbdeheader(0, fs, d.RATE[rate], kbch)
+        out = np.concatenate([r.work(bb) for bb in calls])
+        cases[name] = dict(kbch=kbch, calls=[int(bb.shape[0]) for bb in calls], ts_bytes=int(out.size), sha256=sha(out),
+                           counters=r.counters())
+        print(name, out.size, r.counters())
+    zero = np.zeros((1, 58192 // 8), dtype=np.uint8)
+    prbs = ref.bb_descramble(0, 1, d.RATE["C9_10"], zero)
+    with open(os.path.join(OUT, "bb.json"), "w") as f:
+        json.dump(dict(generator="tools/gen_golden.py",
+                       reference="lib/bbdeheader_bb_impl.cc + lib/bbdescrambler_bb_impl.cc compiled unmodified (oracle/ref_bb_harness.cc)",
+                       prbs_sha256=sha(prbs), cases=cases), f, indent=1)
+
+
 if __name__ == "__main__":
-    gen_ldpc()
-    gen_bch()
-    gen_demap()
+    which = sys.argv[1:] or ["ldpc", "bch", "demap", "bb"]
+    if "ldpc" in which:
+        gen_ldpc()
+    if "bch" in which:
+        gen_bch()
+    if "demap" in which:
+        gen_demap()
+    if "bb" in which:
+        gen_bb()
