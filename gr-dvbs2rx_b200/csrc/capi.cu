@@ -338,6 +338,48 @@ int bits_per_symbol(int constellation)
     return 0;
 }
 
+// 8PSK deinterleaver row offsets by code rate: lib/xfecframe_demapper_cb_impl.cc:48-69
+void rows_8psk(int rate, int rows, int& r0, int& r1, int& r2)
+{
+    if (rate == 4) { // C3_5
+        r0 = rows * 2, r1 = rows, r2 = 0;
+    } else if (rate == 26 || rate == 28 || rate == 38 || rate == 39 || rate == 19) {
+        r0 = rows, r1 = 0, r2 = rows * 2; // C25_36 C13_18 C7_15 C8_15 C26_45
+    } else {
+        r0 = 0, r1 = rows, r2 = rows * 2;
+    }
+}
+
+int snr_dev(dvbs2b200_code* h, int constellation, const float* d_iq, const int8_t* d_llr, int frames, float* d_snr,
+            cudaStream_t stream)
+{
+    const BlobHeader& hd = h->hdr;
+    const int bits = bits_per_symbol(constellation);
+    if (!bits)
+        return fail(DVBS2B200_EUNSUPPORTED, "Unsupported constellation");
+    if (frames < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames");
+    if (frames == 0)
+        return DVBS2B200_OK;
+    if (!d_iq || !d_snr)
+        return fail(DVBS2B200_EINVAL, "null buffer");
+    SnrLaunch p;
+    memset(&p, 0, sizeof(p));
+    p.iq = d_iq;
+    p.llr = d_llr;
+    p.snr_lin = d_snr;
+    p.frames = frames;
+    p.n_syms = hd.N / bits;
+    p.constellation = constellation;
+    if (constellation == 4)
+        rows_8psk(hd.rate, p.n_syms, p.row0, p.row1, p.row2);
+    cudaError_t e = snr_launch(p, stream);
+    if (e != cudaSuccess)
+        return cuda_fail(e, "snr_launch");
+    h->launches += 1;
+    return DVBS2B200_OK;
+}
+
 int demap_dev(dvbs2b200_code* h, int constellation, const float* d_iq, int frames, const float* d_n0, int8_t* d_llr,
               cudaStream_t stream)
 {
@@ -355,16 +397,8 @@ int demap_dev(dvbs2b200_code* h, int constellation, const float* d_iq, int frame
     memset(&p, 0, sizeof(p));
     p.n_syms = hd.N / bits;
     p.constellation = constellation;
-    if (constellation == 4) {
-        const int rows = p.n_syms, rate = hd.rate; // lib/xfecframe_demapper_cb_impl.cc:48-69
-        if (rate == 4) { // C3_5
-            p.row0 = rows * 2, p.row1 = rows, p.row2 = 0;
-        } else if (rate == 26 || rate == 28 || rate == 38 || rate == 39 || rate == 19) {
-            p.row0 = rows, p.row1 = 0, p.row2 = rows * 2; // C25_36 C13_18 C7_15 C8_15 C26_45
-        } else {
-            p.row0 = 0, p.row1 = rows, p.row2 = rows * 2;
-        }
-    }
+    if (constellation == 4)
+        rows_8psk(hd.rate, p.n_syms, p.row0, p.row1, p.row2);
     for (int f0 = 0; f0 < frames; f0 += 32768) { // gridDim.y limit
         p.frames = std::min(32768, frames - f0);
         p.iq = d_iq + (size_t)f0 * p.n_syms * 2;
@@ -989,6 +1023,50 @@ int dvbs2b200_fec_decode(dvbs2b200_code* h, int constellation, const float* iq, 
     CUP(cudaStreamSynchronize(h->stream));
 #undef CUP
     cleanup();
+    return DVBS2B200_OK;
+}
+
+// ---- SNR estimate ---------------------------------------------------------------------------------
+int dvbs2b200_estimate_snr_dev(dvbs2b200_code* h, int constellation, const float* d_iq, const int8_t* d_llr_post, int frames,
+                               float* d_snr_lin, void* stream)
+{
+    if (!h)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    DeviceGuard g(h->device);
+    return snr_dev(h, constellation, d_iq, d_llr_post, frames, d_snr_lin, (cudaStream_t)stream);
+}
+
+int dvbs2b200_estimate_snr(dvbs2b200_code* h, int constellation, const float* iq, const int8_t* llr_post, int frames,
+                           float* snr_lin)
+{
+    if (!h)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    const int bits = bits_per_symbol(constellation);
+    if (!bits)
+        return fail(DVBS2B200_EUNSUPPORTED, "Unsupported constellation");
+    if (frames < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames");
+    if (frames == 0)
+        return DVBS2B200_OK;
+    if (!iq || !snr_lin)
+        return fail(DVBS2B200_EINVAL, "null buffer");
+    DeviceGuard g(h->device);
+    const BlobHeader& hd = h->hdr;
+    const size_t iq_bytes = (size_t)frames * (hd.N / bits) * 8, llr_bytes = (size_t)frames * hd.N;
+    int rc;
+    if ((rc = h->d_in.ensure(iq_bytes)) || (rc = h->d_n0.ensure((size_t)frames * 4)))
+        return rc;
+    if (llr_post && (rc = h->d_llr.ensure(llr_bytes)))
+        return rc;
+    cudaStream_t s = h->stream;
+    CU(cudaMemcpyAsync(h->d_in.p, iq, iq_bytes, cudaMemcpyHostToDevice, s));
+    if (llr_post)
+        CU(cudaMemcpyAsync(h->d_llr.p, llr_post, llr_bytes, cudaMemcpyHostToDevice, s));
+    rc = snr_dev(h, constellation, (const float*)h->d_in.p, llr_post ? (const int8_t*)h->d_llr.p : nullptr, frames, (float*)h->d_n0.p, s);
+    if (rc)
+        return rc;
+    CU(cudaMemcpyAsync(snr_lin, h->d_n0.p, (size_t)frames * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
     return DVBS2B200_OK;
 }
 

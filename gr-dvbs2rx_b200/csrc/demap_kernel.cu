@@ -93,7 +93,71 @@ __global__ void __launch_bounds__(256) demap_8psk_kernel(const DemapLaunch p)
     }
 }
 
+// ---- SNR estimate of one XFECFRAME per CTA (lib/xfecframe_demapper_cb_impl.cc:128-142,267-302; lib/qpsk.h:41-65,
+//      240-281): Es/N0 = sum |ref|^2 / sum |x - ref|^2 with the reference points taken from the sliced symbols
+//      (llr == null) or from the signs of the posterior LLRs.  Floating point sums: tolerance-checked, the
+//      reference's own summation order (VOLK) is unspecified.  HBM bound: 8 bytes per symbol (+ bits per symbol).
+__global__ void __launch_bounds__(256) snr_kernel(const SnrLaunch p)
+{
+    const int frame = blockIdx.x, tid = threadIdx.x;
+    const float2* __restrict__ in = reinterpret_cast<const float2*>(p.iq + (size_t)frame * p.n_syms * 2);
+    const int8_t* __restrict__ llr = p.llr ? p.llr + (size_t)frame * p.n_syms * (p.constellation == 0 ? 2 : 3) : nullptr;
+    const float a = 0.70710678118654752440f;
+    const float rot_re = (float)0.92387953251128675613, rot_im = (float)-0.38268343236508977173;
+    float sp = 0.f, np = 0.f;
+    for (int j = tid; j < p.n_syms; j += 256) {
+        const float2 x = __ldcs(in + j);
+        float sr, si;
+        if (p.constellation == 0) {
+            const bool pr = llr ? llr[2 * j] >= 0 : x.x >= 0.f, pi = llr ? llr[2 * j + 1] >= 0 : x.y >= 0.f;
+            sr = pr ? a : -a;
+            si = pi ? a : -a;
+        } else {
+            bool b0, b1, b2; // true = the bit's LLR is negative
+            if (llr) {
+                b0 = llr[p.row0 + j] < 0, b1 = llr[p.row1 + j] < 0, b2 = llr[p.row2 + j] < 0;
+            } else { // lib/psk.hh:135-141
+                const float re = __fsub_rn(__fmul_rn(x.x, rot_re), __fmul_rn(x.y, rot_im));
+                const float im = __fadd_rn(__fmul_rn(x.x, rot_im), __fmul_rn(x.y, rot_re));
+                b1 = re < 0.f, b2 = im < 0.f, b0 = fabsf(re) < fabsf(im);
+            }
+            // lib/psk.hh:114-121,152-157: index = 4 b0 + 2 b1 + b2
+            const int idx = (b0 ? 4 : 0) | (b1 ? 2 : 0) | (b2 ? 1 : 0);
+            const float tr[8] = { a, 1.f, -1.f, -a, 0.f, a, -a, 0.f }, ti[8] = { a, 0.f, 0.f, -a, 1.f, -a, a, -1.f };
+            sr = tr[idx], si = ti[idx];
+        }
+        const float er = x.x - sr, ei = x.y - si;
+        sp += sr * sr + si * si;
+        np += er * er + ei * ei;
+    }
+    __shared__ float s_sp[8], s_np[8];
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        sp += __shfl_xor_sync(0xffffffffu, sp, m);
+        np += __shfl_xor_sync(0xffffffffu, np, m);
+    }
+    if ((tid & 31) == 0)
+        s_sp[tid >> 5] = sp, s_np[tid >> 5] = np;
+    __syncthreads();
+    if (tid == 0) {
+        float tsp = 0.f, tnp = 0.f;
+        for (int w = 0; w < 8; ++w)
+            tsp += s_sp[w], tnp += s_np[w];
+        if (!(tnp > 0.f))
+            tnp = 1e-12f;
+        p.snr_lin[frame] = tsp / tnp;
+    }
+}
+
 } // namespace
+
+cudaError_t snr_launch(const SnrLaunch& p, cudaStream_t stream)
+{
+    if (p.frames <= 0)
+        return cudaSuccess;
+    snr_kernel<<<p.frames, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
 
 cudaError_t demap_launch(const DemapLaunch& p, cudaStream_t stream)
 {

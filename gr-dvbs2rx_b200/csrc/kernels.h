@@ -76,6 +76,16 @@ struct DemapLaunch {
 };
 cudaError_t demap_launch(const DemapLaunch& p, cudaStream_t stream);
 
+struct SnrLaunch {
+    const float* iq;   // [frames][n_syms][2]
+    const int8_t* llr; // null: slice the symbols; else [frames][N] posterior LLRs (codeword order)
+    float* snr_lin;    // [frames] linear Es/N0
+    int frames, n_syms;
+    int constellation; // 0 QPSK, 4 8PSK
+    int row0, row1, row2;
+};
+cudaError_t snr_launch(const SnrLaunch& p, cudaStream_t stream);
+
 // ---- BB layer: descrambler + deheader (bb_kernel.cu) --------------------------------------------------
 // Stream state of the deheader (lib/bbdeheader_bb_impl.h:40-53), in device memory, one per handle.
 struct BbState {

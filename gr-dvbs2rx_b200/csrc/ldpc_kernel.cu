@@ -1125,6 +1125,8 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = TMEM ? s_tmem_base : 0u;
     const uint32_t tmem_warp = tmem_base + ((uint32_t)((tid >> 5) & 3) << 21); // this warp's 32 TMEM lanes
+    (void)tmem_warp;
+    (void)tcol;
     // stage the code tables once per CTA (TMA)
     if (tid == 0) {
         mbar_expect_tx(bar, p.tab_bytes);

@@ -75,6 +75,8 @@ _SIGS = {
     "dvbs2b200_demap_dev": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, _P]),
     "dvbs2b200_fec_decode": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "dvbs2b200_fec_decode_dev": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "dvbs2b200_estimate_snr": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P]),
+    "dvbs2b200_estimate_snr_dev": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, _P]),
     "dvbs2b200_bb_descramble": (C.c_int, [_P, _P, C.c_int, _P]),
     "dvbs2b200_bb_descramble_dev": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "dvbs2b200_bb_ts_capacity": (C.c_size_t, [_P, C.c_int]),
@@ -254,6 +256,22 @@ class Code:
         _check(lib().dvbs2b200_fec_decode(self._h, constellation, _ptr(iq), _ptr(n0), _ptr(llr), F, max_trials,
                                           term_group, msg.ctypes.data, trials.ctypes.data, corr.ctypes.data))
         return msg, trials, corr
+
+    def estimate_snr(self, constellation, iq, llr_post=None):
+        """Linear Es/N0 per frame: from sliced symbols, or from posterior LLR signs when given."""
+        bits = bits_per_symbol(constellation)
+        if not bits:
+            raise Dvbs2Error(EUNSUPPORTED, "Unsupported constellation")
+        iq = _np(iq, np.float32).reshape(-1, self.N // bits, 2)
+        F = iq.shape[0]
+        if llr_post is not None:
+            llr_post = _np(llr_post, np.int8).reshape(F, self.N)
+        out = np.empty(F, dtype=np.float32)
+        _check(lib().dvbs2b200_estimate_snr(self._h, constellation, iq.ctypes.data, _ptr(llr_post), F, out.ctypes.data))
+        return out
+
+    def estimate_snr_dev(self, constellation, d_iq, d_llr_post, frames, d_snr, stream):
+        _check(lib().dvbs2b200_estimate_snr_dev(self._h, constellation, d_iq, d_llr_post, frames, d_snr, stream))
 
     # ---- BB layer: BBFRAMEs -> TS packets (bbdescrambler_bb / bbdeheader_bb) ---------------------
     def bb_descramble(self, bbframes):

@@ -263,64 +263,9 @@ void xfecframe_demapper_cb::forecast(int noutput_items, gr_vector_int& ninput_it
     ninput_items_required[0] = noutput_items / d_bits;
 }
 
-namespace {
-const float SQRT2_2 = 0.70710678118654752440f;
-// lib/psk.hh:135-141 hard + :152-157 map for 8PSK
-inline gr_complex slice_8psk(gr_complex c)
-{
-    static const gr_complex m_8psk[8] = { { SQRT2_2, SQRT2_2 }, { 1, 0 }, { -1, 0 }, { -SQRT2_2, -SQRT2_2 },
-                                          { 0, 1 }, { SQRT2_2, -SQRT2_2 }, { -SQRT2_2, SQRT2_2 }, { 0, -1 } };
-    const gr_complex rot((float)std::cos(-M_PI / 8), (float)std::sin(-M_PI / 8));
-    c *= rot;
-    int b1 = c.real() < 0, b2 = c.imag() < 0, b0 = std::abs(c.real()) < std::abs(c.imag());
-    return m_8psk[(b0 << 2) | (b1 << 1) | b2];
-}
-inline gr_complex map_8psk_bits(int b0, int b1, int b2)
-{
-    static const gr_complex m_8psk[8] = { { SQRT2_2, SQRT2_2 }, { 1, 0 }, { -1, 0 }, { -SQRT2_2, -SQRT2_2 },
-                                          { 0, 1 }, { SQRT2_2, -SQRT2_2 }, { -SQRT2_2, SQRT2_2 }, { 0, -1 } };
-    return m_8psk[(b0 << 2) | (b1 << 1) | b2];
-}
-} // namespace
 
-// lib/qpsk.h:240-244,41-65 (QPSK) / lib/xfecframe_demapper_cb_impl.cc:131-145 (8PSK): Es/N0 from hard slices
-float xfecframe_demapper_cb::estimate_snr_symbols(const gr_complex* in) const
-{
-    float sp = 0, np = 0;
-    for (unsigned int j = 0; j < d_xfecframe_len; j++) {
-        gr_complex s;
-        if (d_constellation == MOD_QPSK)
-            s = gr_complex(in[j].real() >= 0 ? SQRT2_2 : -SQRT2_2, in[j].imag() >= 0 ? SQRT2_2 : -SQRT2_2);
-        else
-            s = slice_8psk(in[j]);
-        sp += std::norm(s);
-        np += std::norm(in[j] - s);
-    }
-    if (!(np > 0))
-        np = 1e-12f;
-    return sp / np;
-}
-
-// post-decoder estimate: reference points rebuilt from the posterior LLR signs
-// (lib/qpsk.h:267-281; lib/xfecframe_demapper_cb_impl.cc:270-305 for 8PSK)
-float xfecframe_demapper_cb::estimate_snr_llr(const gr_complex* in, const int8_t* llr) const
-{
-    float sp = 0, np = 0;
-    for (unsigned int j = 0; j < d_xfecframe_len; j++) {
-        gr_complex s;
-        if (d_constellation == MOD_QPSK) {
-            s = gr_complex(llr[2 * j] >= 0 ? SQRT2_2 : -SQRT2_2, llr[2 * j + 1] >= 0 ? SQRT2_2 : -SQRT2_2);
-        } else {
-            s = map_8psk_bits(llr[d_rowaddr0 + j] < 0, llr[d_rowaddr1 + j] < 0, llr[d_rowaddr2 + j] < 0);
-        }
-        sp += std::norm(s);
-        np += std::norm(in[j] - s);
-    }
-    if (!(np > 0))
-        np = 1e-12f;
-    return sp / np;
-}
-
+// The SNR estimates (lib/qpsk.h:240-281, lib/xfecframe_demapper_cb_impl.cc:128-142,267-302) run on the GPU:
+// dvbs2b200_estimate_snr, one launch per general_work call / per PDU.
 int xfecframe_demapper_cb::general_work(int noutput_items, gr_vector_int& /*ninput_items*/,
                                         gr_vector_const_void_star& input_items, gr_vector_void_star& output_items)
 {
@@ -330,12 +275,20 @@ int xfecframe_demapper_cb::general_work(int noutput_items, gr_vector_int& /*ninp
     const int n_frames = noutput_items / d_fecframe_len;
     d_n0_per_frame.resize(std::max(n_frames, 1));
     const gr_complex* p = in;
+    // initial SNR estimates of the whole call in one launch (lib/xfecframe_demapper_cb_impl.cc:123-146)
+    if (d_waiting_first_llr && n_frames > 0) {
+        d_snr_per_frame.resize(n_frames);
+        int rc = dvbs2b200_estimate_snr(d_code, d_constellation, reinterpret_cast<const float*>(in), nullptr, n_frames,
+                                        d_snr_per_frame.data());
+        if (rc != DVBS2B200_OK)
+            throw std::runtime_error(std::string("dvbs2b200_estimate_snr: ") + dvbs2b200_last_error());
+    }
     for (int i = 0; i < n_frames; i++) { // lib/xfecframe_demapper_cb_impl.cc:115-149
         d_saved[d_idx] = d_frame_cnt;
         memcpy(d_pool[d_idx].data(), p, d_xfecframe_len * sizeof(gr_complex));
         d_idx = (d_idx + 1) % kPool;
         if (d_waiting_first_llr) {
-            float snr_lin = estimate_snr_symbols(p);
+            float snr_lin = d_snr_per_frame[i];
             d_snr = 10 * std::log10(snr_lin);
             d_N0 = 1.0f / snr_lin;
             d_precision = 4.0 / d_N0;
@@ -360,6 +313,9 @@ void xfecframe_demapper_cb::handle_llr_pdu(const llr_pdu& pdu)
         return; // the reference logs and drops malformed PDUs (:193-242)
     size_t n_frames = pdu.n_llr / d_fecframe_len, n_processed = 0;
     float accum = 0;
+    // gather the saved XFECFRAMEs of the PDU's frames, then one launch for all of them (:252-310)
+    d_gather_iq.clear();
+    d_gather_llr.clear();
     for (size_t i = 0; i < n_frames; i++) {
         size_t idx = kPool;
         for (size_t k = 0; k < kPool; k++)
@@ -369,8 +325,18 @@ void xfecframe_demapper_cb::handle_llr_pdu(const llr_pdu& pdu)
             }
         if (idx == kPool)
             continue;
-        accum += estimate_snr_llr(d_pool[idx].data(), pdu.llr + i * d_fecframe_len);
+        d_gather_iq.insert(d_gather_iq.end(), d_pool[idx].begin(), d_pool[idx].end());
+        d_gather_llr.insert(d_gather_llr.end(), pdu.llr + i * d_fecframe_len, pdu.llr + (i + 1) * d_fecframe_len);
         n_processed++;
+    }
+    if (n_processed > 0) {
+        d_snr_per_frame.resize(n_processed);
+        int rc = dvbs2b200_estimate_snr(d_code, d_constellation, reinterpret_cast<const float*>(d_gather_iq.data()),
+                                        d_gather_llr.data(), (int)n_processed, d_snr_per_frame.data());
+        if (rc != DVBS2B200_OK)
+            throw std::runtime_error(std::string("dvbs2b200_estimate_snr: ") + dvbs2b200_last_error());
+        for (size_t i = 0; i < n_processed; i++)
+            accum += d_snr_per_frame[i];
     }
     float avg = accum / n_processed; // :312-317 (NaN when nothing was processed, as the reference)
     d_snr = 10 * std::log10(avg);

@@ -129,8 +129,6 @@ public:
 
 private:
     xfecframe_demapper_cb() {}
-    float estimate_snr_symbols(const gr_complex* in) const;
-    float estimate_snr_llr(const gr_complex* in, const int8_t* llr) const;
     dvbs2b200_code* d_code = nullptr;
     dvb_constellation_t d_constellation;
     dvb_code_rate_t d_rate;
@@ -145,7 +143,9 @@ private:
     std::array<std::vector<gr_complex>, kPool> d_pool;
     std::array<uint64_t, kPool> d_saved;
     size_t d_idx = 0;
-    std::vector<float> d_n0_per_frame;
+    std::vector<float> d_n0_per_frame, d_snr_per_frame;
+    std::vector<gr_complex> d_gather_iq;
+    std::vector<int8_t> d_gather_llr;
 };
 
 // bbdescrambler_bb <- include/gnuradio/dvbs2rx/bbdescrambler_bb.h, lib/bbdescrambler_bb_impl.{h,cc} (a gr::sync_block)

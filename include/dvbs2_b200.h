@@ -143,6 +143,20 @@ int dvbs2b200_demap(dvbs2b200_code* h, int constellation, const float* iq, int f
 int dvbs2b200_demap_dev(dvbs2b200_code* h, int constellation, const float* d_iq, int frames,
                         const float* d_n0, int8_t* d_llr, void* stream);
 
+/* ---- SNR estimate of the demapper block ------------------------------------------------------- */
+/* dvbs2b200_estimate_snr <- the initial estimate in general_work  lib/xfecframe_demapper_cb_impl.cc:123-146
+ *                           (QpskConstellation::estimate_snr      lib/qpsk.h:240-244, PSK hard/map lib/psk.hh:135-157)
+ *                           and the refinement in handle_llr_pdu   lib/xfecframe_demapper_cb_impl.cc:252-318
+ *                           (QpskConstellation::estimate_snr(llr)  lib/qpsk.h:267-281)
+ * snr_lin[f] = sum |ref|^2 / sum |x - ref|^2 of frame f (linear Es/N0; the block keeps 10 log10 of it as
+ * get_snr() and N0 = 1 / snr_lin).  llr_post == NULL: reference points by slicing the symbols; else from
+ * the signs of the posterior LLRs [frames][n_ldpc] that the LDPC decoder publishes on "llr_pdu".
+ * Floating-point sums: agreement with the reference is to tolerance (its VOLK sums have no fixed order). */
+int dvbs2b200_estimate_snr(dvbs2b200_code* h, int constellation, const float* iq, const int8_t* llr_post,
+                           int frames, float* snr_lin);
+int dvbs2b200_estimate_snr_dev(dvbs2b200_code* h, int constellation, const float* d_iq,
+                               const int8_t* d_llr_post, int frames, float* d_snr_lin, void* stream);
+
 /* ---- fused chain: LLRs (or symbols) in, BBFRAME bytes out ---------------------------------- */
 /* Runs [demap ->] LDPC (OM_MESSAGE) -> BCH with intermediates kept in device memory.
  * iq == NULL: start from llr.  msg [frames][kbch/8]; status arrays may be NULL. */

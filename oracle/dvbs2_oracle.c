@@ -673,6 +673,65 @@ void orc_demap_8psk(const float* iq, int n_syms, float n0, int rate, int8_t* llr
 }
 
 /* ------------------------------------------------------------------------------------- */
+/* SNR estimates of the demapper block -- tolerance-checked, not bit-exact:
+ * the reference sums with VOLK dot products whose order is unspecified (lib/qpsk.h:41-65).   */
+/* ------------------------------------------------------------------------------------- */
+/* QPSK: reference points by slicing the symbols (llr == NULL, lib/qpsk.h:171-181,240-244: a
+ * component >= 0 maps to +sqrt(2)/2) or the posterior LLRs (lib/qpsk.h:267-281).  Es/N0 linear. */
+float orc_snr_qpsk(const float* iq, int n_syms, const int8_t* llr)
+{
+    const float a = 0.70710678118654752440f;
+    double sp = 0, np = 0;
+    for (int i = 0; i < 2 * n_syms; ++i) {
+        const int pos = llr ? (llr[i] >= 0) : (iq[i] >= 0.0f);
+        const float r = pos ? a : -a;
+        const float e = iq[i] - r;
+        sp += (double)r * r;
+        np += (double)e * e;
+    }
+    if (np == 0)
+        np = 1e-12;
+    return (float)(sp / np);
+}
+
+/* 8PSK: lib/xfecframe_demapper_cb_impl.cc:128-142 (hard slice, lib/psk.hh:135-141) and :267-302
+ * (posterior LLR signs through the deinterleaver rows); constellation lib/psk.hh:114-121,152-157. */
+float orc_snr_8psk(const float* iq, int n_syms, const int8_t* llr, int rate)
+{
+    static const float m8[8][2] = { { 0.70710678118654752440f, 0.70710678118654752440f }, { 1, 0 }, { -1, 0 },
+                                    { -0.70710678118654752440f, -0.70710678118654752440f }, { 0, 1 },
+                                    { 0.70710678118654752440f, -0.70710678118654752440f },
+                                    { -0.70710678118654752440f, 0.70710678118654752440f }, { 0, -1 } };
+    const float rot_re = (float)cos(-M_PI / 8), rot_im = (float)sin(-M_PI / 8);
+    int rows = n_syms, r0, r1, r2;
+    if (rate == 4) {
+        r0 = rows * 2; r1 = rows; r2 = 0;
+    } else if (rate == 26 || rate == 28 || rate == 38 || rate == 39 || rate == 19) {
+        r0 = rows; r1 = 0; r2 = rows * 2;
+    } else {
+        r0 = 0; r1 = rows; r2 = rows * 2;
+    }
+    float sp = 0, np = 0;
+    for (int j = 0; j < n_syms; ++j) {
+        const float a = iq[2 * j], b = iq[2 * j + 1];
+        int b0, b1, b2; /* 1 = negative */
+        if (llr) {
+            b0 = llr[r0 + j] < 0; b1 = llr[r1 + j] < 0; b2 = llr[r2 + j] < 0;
+        } else {
+            const float re = a * rot_re - b * rot_im, im = a * rot_im + b * rot_re;
+            b1 = re < 0; b2 = im < 0; b0 = fabsf(re) < fabsf(im);
+        }
+        const float* s = m8[4 * b0 + 2 * b1 + b2];
+        const float er = a - s[0], ei = b - s[1];
+        sp += s[0] * s[0] + s[1] * s[1];
+        np += er * er + ei * ei;
+    }
+    if (!(np > 0))
+        np = 1e-12f;
+    return sp / np;
+}
+
+/* ------------------------------------------------------------------------------------- */
 /* BB layer: descrambler and deheader                                   */
 /* ------------------------------------------------------------------------------------- */
 /* lib/bbdescrambler_bb_impl.cc:51-65: the PRBS 1 + x^14 + x^15, register loaded with

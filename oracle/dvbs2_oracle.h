@@ -75,6 +75,12 @@ void orc_demap_qpsk(const float* iq, int n_syms, float n0, int8_t* llr);
 /* soft demap + 3-column deinterleave; rate picks the column order */
 void orc_demap_8psk(const float* iq, int n_syms, float n0, int rate, int8_t* llr);
 
+/* ---- SNR estimates (lib/qpsk.h:41-65,240-281; lib/xfecframe_demapper_cb_impl.cc:128-142,267-302):
+ * linear Es/N0 of one frame; llr == NULL slices the symbols, else the posterior LLR signs give the
+ * reference points.  Tolerance-checked only (VOLK summation order is unspecified). */
+float orc_snr_qpsk(const float* iq, int n_syms, const int8_t* llr);
+float orc_snr_8psk(const float* iq, int n_syms, const int8_t* llr, int rate);
+
 /* ---- BB layer (lib/bbdescrambler_bb_impl.cc:51-82, lib/bbdeheader_bb_impl.cc:76-261) -------
  * Pinned against the reference's two translation units compiled unmodified over a 60-line
  * gr::block shim (oracle/ref_bb_harness.cc, oracle/shim/gnuradio/block.h) and against the

@@ -267,6 +267,33 @@ void ref_demap_8psk(const float* iq, int n_syms, float n0, int r0, int r1, int r
         out[r2 + j] = soft[idx++];
     }
 }
+/* ---- 8PSK SNR estimates: lib/psk.hh hard()/map() driven as the block does.  llr == NULL: the initial
+ *      estimate from sliced symbols (lib/xfecframe_demapper_cb_impl.cc:128-142); else the post-decoder one
+ *      from posterior LLR signs, re-interleaved through the row offsets (:267-302).  Returns sp / np. */
+float ref_snr_8psk(const float* iq, int n_syms, const int8_t* llr, int r0, int r1, int r2)
+{
+    PhaseShiftKeying<8, gr_complex, int8_t> mod;
+    Modulation<gr_complex, int8_t>* m = &mod;
+    const gr_complex* in = reinterpret_cast<const gr_complex*>(iq);
+    float sp = 0, np = 0;
+    int8_t tmp[3];
+    for (int j = 0; j < n_syms; ++j) {
+        if (llr) {
+            tmp[0] = llr[r0 + j] < 0 ? -1 : 1;
+            tmp[1] = llr[r1 + j] < 0 ? -1 : 1;
+            tmp[2] = llr[r2 + j] < 0 ? -1 : 1;
+        } else {
+            m->hard(tmp, in[j]);
+        }
+        gr_complex s = m->map(tmp);
+        gr_complex e = in[j] - s;
+        sp += std::norm(s);
+        np += std::norm(e);
+    }
+    if (!(np > 0))
+        np = 1e-12;
+    return sp / np;
+}
 /* QPSK through the generic PSK class (lib/psk.hh:87-91); the block itself uses VOLK */
 void ref_demap_qpsk_psk4(const float* iq, int n_syms, float precision, int8_t* out)
 {

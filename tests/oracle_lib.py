@@ -71,6 +71,10 @@ class Oracle:
         l.orc_bch_err_loc_numbers.argtypes = [_P, _P, C.c_int, _P]
         l.orc_demap_qpsk.argtypes = [_P, C.c_int, C.c_float, _P]
         l.orc_demap_8psk.argtypes = [_P, C.c_int, C.c_float, C.c_int, _P]
+        l.orc_snr_qpsk.argtypes = [_P, C.c_int, _P]
+        l.orc_snr_qpsk.restype = C.c_float
+        l.orc_snr_8psk.argtypes = [_P, C.c_int, _P, C.c_int]
+        l.orc_snr_8psk.restype = C.c_float
         l.orc_bb_prbs.argtypes = [_P, C.c_int]
         l.orc_bb_descramble.argtypes = [_P, C.c_int, C.c_int, _P]
         l.orc_crc8.argtypes = [_P, C.c_int]
@@ -83,6 +87,19 @@ class Oracle:
         l.orc_bbdeheader_counters.argtypes = [_P, _P]
         self._ldpc = {}
         self._bch = {}
+
+    def estimate_snr(self, constellation, iq, llr=None, rate=0):
+        """Linear Es/N0 per frame (constellation 0 = QPSK, 4 = 8PSK); llr: posterior LLRs or None."""
+        iq = np.ascontiguousarray(iq, dtype=np.float32)
+        F, n_syms = iq.shape[0], iq.shape[1]
+        out = np.zeros(F, dtype=np.float32)
+        for f in range(F):
+            lp = None if llr is None else np.ascontiguousarray(llr[f], dtype=np.int8)
+            if constellation == 0:
+                out[f] = self.l.orc_snr_qpsk(iq[f].ctypes.data, n_syms, _p(lp))
+            else:
+                out[f] = self.l.orc_snr_8psk(iq[f].ctypes.data, n_syms, _p(lp), rate)
+        return out
 
     # ---- BB layer ----
     def bb_prbs(self, nbytes):
@@ -255,6 +272,8 @@ class Ref:
         l.ref_bch_decode_mt.restype = C.c_double
         l.ref_demap_8psk.argtypes = [_P, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, _P]
         l.ref_demap_qpsk_psk4.argtypes = [_P, C.c_int, C.c_float, _P]
+        l.ref_snr_8psk.argtypes = [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int]
+        l.ref_snr_8psk.restype = C.c_float
         l.ref_bb_descramble.argtypes = [C.c_int, C.c_int, C.c_int, _P, C.c_int, _P]
         l.ref_bbdeheader_create.restype = _P
         l.ref_bbdeheader_create.argtypes = [C.c_int, C.c_int, C.c_int]
@@ -262,6 +281,15 @@ class Ref:
         l.ref_bbdeheader_work.argtypes = [_P, _P, C.c_int, _P, C.c_int]
         l.ref_bbdeheader_counters.argtypes = [_P, _P]
         self._init = {}
+
+    def snr_8psk(self, iq, llr, rows):
+        """lib/psk.hh hard()/map() driven as the demapper block does; rows = (r0, r1, r2)."""
+        iq = np.ascontiguousarray(iq, dtype=np.float32)
+        out = np.zeros(iq.shape[0], dtype=np.float32)
+        for f in range(iq.shape[0]):
+            lp = None if llr is None else np.ascontiguousarray(llr[f], dtype=np.int8)
+            out[f] = self.l.ref_snr_8psk(iq[f].ctypes.data, iq.shape[1], _p(lp), *rows)
+        return out
 
     # ---- BB layer: the reference's own blocks over the gr::block shim ----
     def bb_descramble(self, standard, framesize, rate, bbframes):

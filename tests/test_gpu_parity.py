@@ -174,3 +174,32 @@ def test_tables_roundtrip_create_from_blob(gpu):
     assert np.array_equal(ha, hb) and np.array_equal(ta, tb)
     a.close()
     b.close()
+
+
+def test_snr_estimate_matches_oracle(gpu, oracle):
+    """dvbs2b200_estimate_snr (GPU) vs the oracle, QPSK and 8PSK, from sliced symbols and from posterior
+    LLR signs.  Tolerance 1e-4 relative: float sums, the reference's own order (VOLK) is unspecified."""
+    d = gpu
+    from dvbs2rx_b200 import vectors
+    rng = np.random.default_rng(41)
+    for mod, rate_name, esn0 in ((d.MOD_QPSK, "C1_2", 1.0), (d.MOD_QPSK, "C3_4", 9.0), (d.MOD_8PSK, "C3_5", 6.2),
+                                 (d.MOD_8PSK, "C2_3", 12.0), (d.MOD_8PSK, "C25_36", 8.0)):
+        fs = 2 if rate_name == "C25_36" else 1
+        std = 0
+        rate = d.RATE[rate_name]
+        if rate_name == "C25_36":
+            fs = 1
+        msg, cw, info = vectors.encode_frames(std, fs, rate, 5, rng)
+        iq, n0 = vectors.awgn(vectors.map_symbols(cw, mod, rate), esn0, rng)
+        code = d.Code(std, fs, rate)
+        llr = ((1 - 2 * cw.astype(np.int16)) * rng.integers(1, 100, size=cw.shape)).astype(np.int8)
+        llr[:, ::977] = 0  # a zero LLR counts as positive
+        for l in (None, llr):
+            got = code.estimate_snr(mod, iq, l)
+            want = oracle.estimate_snr(mod, iq, l, rate)
+            assert np.allclose(got, want, rtol=1e-4), (rate_name, got, want)
+        # with the transmitted bits as reference the estimate is the channel Es/N0
+        assert np.allclose(10 * np.log10(code.estimate_snr(mod, iq, llr)), esn0, atol=0.3)
+        code.close()
+    with pytest.raises(d.Dvbs2Error):
+        d.Code(0, 1, d.C1_2).estimate_snr(d.MOD_16APSK, np.zeros((1, 16200, 2), np.float32))

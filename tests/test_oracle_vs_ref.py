@@ -68,3 +68,21 @@ def test_bch_all_dvb_parameter_sets(oracle, ref):
             assert np.array_equal(ro, rr), key
             assert np.array_equal(mo, mr), key
     assert len(seen) >= 30
+
+
+def test_snr_8psk_estimates_against_psk_hh(oracle, ref):
+    """orc_snr_8psk vs lib/psk.hh hard()/map() driven as lib/xfecframe_demapper_cb_impl.cc:128-142,267-302."""
+    import dvbs2rx_b200 as d
+    from dvbs2rx_b200 import vectors
+    rng = np.random.default_rng(31)
+    for rate_name in ("C3_5", "C2_3", "C25_36"):
+        rate = d.RATE[rate_name]
+        msg, cw, info = vectors.encode_frames(0, 1, rate, 2, rng)
+        iq, n0 = vectors.awgn(vectors.map_symbols(cw, d.MOD_8PSK, rate), 7.0, rng)
+        rows = vectors.rows_8psk(rate, 21600)
+        llr = (1 - 2 * cw.astype(np.int8)) * 9
+        for l in (None, llr):
+            a, b = oracle.estimate_snr(4, iq, l, rate), ref.snr_8psk(iq, l, rows)
+            assert np.allclose(a, b, rtol=1e-5), (rate_name, a, b)
+        # with the true bits as reference the estimate is the channel's Es/N0
+        assert np.allclose(10 * np.log10(oracle.estimate_snr(4, iq, llr, rate)), 7.0, atol=0.1)
