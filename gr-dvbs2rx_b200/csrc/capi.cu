@@ -88,6 +88,18 @@ struct dvbs2b200_code {
     bool bb_ready = false;
 };
 
+// A set of codes on one device for mixed-MODCOD (VCM/ACM) batches.
+struct dvbs2b200_mixed {
+    int device = 0;
+    std::vector<dvbs2b200_code*> codes;
+    cudaStream_t stream = nullptr; // batch-wide copies
+    DevBuf d_in, d_out, d_tr, d_co;
+    struct PerCode {
+        DevBuf d_in_off, d_out_off, d_pos, d_stage_in, d_stage_out, d_tr, d_co;
+    };
+    std::vector<PerCode> per;
+};
+
 namespace {
 
 void info_from_header(const BlobHeader& h, dvbs2b200_code_info* info)
@@ -1024,6 +1036,174 @@ int dvbs2b200_fec_decode(dvbs2b200_code* h, int constellation, const float* iq, 
 #undef CUP
     cleanup();
     return DVBS2B200_OK;
+}
+
+// ---- mixed-MODCOD batches -------------------------------------------------------------------------------
+int dvbs2b200_mixed_create(dvbs2b200_mixed** out, int device, int n_codes, const int* standard, const int* framesize,
+                           const int* rate)
+{
+    if (!out || n_codes <= 0 || n_codes > 255 || !standard || !framesize || !rate)
+        return fail(DVBS2B200_EINVAL, "bad argument");
+    *out = nullptr;
+    dvbs2b200_mixed* m = new (std::nothrow) dvbs2b200_mixed();
+    if (!m)
+        return fail(DVBS2B200_ENOMEM, "out of host memory");
+    m->device = device;
+    for (int c = 0; c < n_codes; ++c) {
+        dvbs2b200_code* h = nullptr;
+        int rc = dvbs2b200_code_create(&h, device, standard[c], framesize[c], rate[c]);
+        if (rc) {
+            dvbs2b200_mixed_destroy(m);
+            return rc;
+        }
+        m->codes.push_back(h);
+    }
+    m->per.resize(n_codes);
+    DeviceGuard g(device);
+    cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        dvbs2b200_mixed_destroy(m);
+        return cuda_fail(e, "cudaStreamCreate");
+    }
+    *out = m;
+    return DVBS2B200_OK;
+}
+
+void dvbs2b200_mixed_destroy(dvbs2b200_mixed* m)
+{
+    if (!m)
+        return;
+    {
+        DeviceGuard g(m->device);
+        if (m->stream) {
+            cudaStreamSynchronize(m->stream);
+            cudaStreamDestroy(m->stream);
+        }
+        for (DevBuf* b : { &m->d_in, &m->d_out, &m->d_tr, &m->d_co })
+            b->release();
+        for (auto& pc : m->per)
+            for (DevBuf* b : { &pc.d_in_off, &pc.d_out_off, &pc.d_pos, &pc.d_stage_in, &pc.d_stage_out, &pc.d_tr, &pc.d_co })
+                b->release();
+    }
+    for (dvbs2b200_code* h : m->codes)
+        dvbs2b200_code_destroy(h);
+    delete m;
+}
+
+int dvbs2b200_mixed_code_info(const dvbs2b200_mixed* m, int code, dvbs2b200_code_info* info)
+{
+    if (!m || code < 0 || code >= (int)m->codes.size())
+        return fail(DVBS2B200_EINVAL, "bad argument");
+    return dvbs2b200_code_info_get(m->codes[code], info);
+}
+
+int dvbs2b200_mixed_fec_decode(dvbs2b200_mixed* m, int frames, const uint8_t* code_id, const int8_t* llr, int max_trials,
+                               uint8_t* msg, int32_t* trials_left, int32_t* corrections)
+{
+    if (!m)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    if (frames < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames");
+    if (frames == 0)
+        return DVBS2B200_OK;
+    if (!code_id || !llr || !msg)
+        return fail(DVBS2B200_EINVAL, "null buffer");
+    DeviceGuard g(m->device);
+    const int nc = (int)m->codes.size();
+    // bucket the frames by code: byte offsets into the concatenated input / output, positions in the batch
+    std::vector<std::vector<unsigned long long>> in_off(nc), out_off(nc);
+    std::vector<std::vector<int32_t>> pos(nc);
+    unsigned long long in_total = 0, out_total = 0;
+    for (int f = 0; f < frames; ++f) {
+        const int c = code_id[f];
+        if (c >= nc)
+            return fail(DVBS2B200_EINVAL, "code_id out of range");
+        const BlobHeader& hd = m->codes[c]->hdr;
+        in_off[c].push_back(in_total);
+        out_off[c].push_back(out_total);
+        pos[c].push_back(f);
+        in_total += (unsigned long long)hd.N;
+        out_total += (unsigned long long)hd.kbch / 8;
+    }
+    int rc;
+    if ((rc = m->d_in.ensure(in_total)) || (rc = m->d_out.ensure(out_total)) || (rc = m->d_tr.ensure((size_t)frames * 4)) ||
+        (rc = m->d_co.ensure((size_t)frames * 4)))
+        return rc;
+    cudaEvent_t ev_in = nullptr;
+    std::vector<cudaEvent_t> ev_done(nc, nullptr);
+    auto cleanup = [&]() {
+        if (ev_in)
+            cudaEventDestroy(ev_in);
+        for (cudaEvent_t e : ev_done)
+            if (e)
+                cudaEventDestroy(e);
+    };
+#define CUM(call)                                \
+    do {                                         \
+        cudaError_t e__ = (call);                \
+        if (e__ != cudaSuccess) {                \
+            cudaDeviceSynchronize();             \
+            cleanup();                           \
+            return cuda_fail(e__, #call);        \
+        }                                        \
+    } while (0)
+    CUM(cudaMemcpyAsync(m->d_in.p, llr, in_total, cudaMemcpyHostToDevice, m->stream));
+    CUM(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+    CUM(cudaEventRecord(ev_in, m->stream));
+    for (int c = 0; c < nc; ++c) {
+        const int n = (int)pos[c].size();
+        if (n == 0)
+            continue;
+        dvbs2b200_code* h = m->codes[c];
+        const BlobHeader& hd = h->hdr;
+        auto& pc = m->per[c];
+        const int kb = hd.kbch / 8;
+        if ((rc = pc.d_in_off.ensure((size_t)n * 8)) || (rc = pc.d_out_off.ensure((size_t)n * 8)) || (rc = pc.d_pos.ensure((size_t)n * 4)) ||
+            (rc = pc.d_stage_in.ensure((size_t)n * hd.N)) || (rc = pc.d_stage_out.ensure((size_t)n * kb)) ||
+            (rc = pc.d_tr.ensure((size_t)n * 4)) || (rc = pc.d_co.ensure((size_t)n * 4))) {
+            cudaDeviceSynchronize();
+            cleanup();
+            return rc;
+        }
+        cudaStream_t s = h->stream; // every code decodes on its own stream: the codes of a batch overlap
+        CUM(cudaMemcpyAsync(pc.d_in_off.p, in_off[c].data(), (size_t)n * 8, cudaMemcpyHostToDevice, s));
+        CUM(cudaMemcpyAsync(pc.d_out_off.p, out_off[c].data(), (size_t)n * 8, cudaMemcpyHostToDevice, s));
+        CUM(cudaMemcpyAsync(pc.d_pos.p, pos[c].data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        CUM(cudaStreamWaitEvent(s, ev_in, 0));
+        CUM(gather_launch((const uint8_t*)m->d_in.p, (const unsigned long long*)pc.d_in_off.p, (uint8_t*)pc.d_stage_in.p, hd.N, n, s));
+        rc = dvbs2b200_fec_decode_dev(h, 0, nullptr, nullptr, (const int8_t*)pc.d_stage_in.p, n, max_trials, 0, (uint8_t*)pc.d_stage_out.p,
+                                      (int32_t*)pc.d_tr.p, (int32_t*)pc.d_co.p, s);
+        if (rc) {
+            cudaDeviceSynchronize();
+            cleanup();
+            return rc;
+        }
+        CUM(scatter_launch((const uint8_t*)pc.d_stage_out.p, (const unsigned long long*)pc.d_out_off.p, (uint8_t*)m->d_out.p, kb, n,
+                           (const int32_t*)pc.d_tr.p, (const int32_t*)pc.d_co.p, (const int32_t*)pc.d_pos.p, (int32_t*)m->d_tr.p,
+                           (int32_t*)m->d_co.p, s));
+        h->launches += 2;
+        CUM(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
+        CUM(cudaEventRecord(ev_done[c], s));
+        CUM(cudaStreamWaitEvent(m->stream, ev_done[c], 0));
+    }
+    CUM(cudaMemcpyAsync(msg, m->d_out.p, out_total, cudaMemcpyDeviceToHost, m->stream));
+    if (trials_left)
+        CUM(cudaMemcpyAsync(trials_left, m->d_tr.p, (size_t)frames * 4, cudaMemcpyDeviceToHost, m->stream));
+    if (corrections)
+        CUM(cudaMemcpyAsync(corrections, m->d_co.p, (size_t)frames * 4, cudaMemcpyDeviceToHost, m->stream));
+    CUM(cudaStreamSynchronize(m->stream));
+#undef CUM
+    cleanup();
+    return DVBS2B200_OK;
+}
+
+uint64_t dvbs2b200_mixed_launch_count(const dvbs2b200_mixed* m)
+{
+    uint64_t n = 0;
+    if (m)
+        for (const dvbs2b200_code* h : m->codes)
+            n += h->launches;
+    return n;
 }
 
 // ---- SNR estimate ---------------------------------------------------------------------------------

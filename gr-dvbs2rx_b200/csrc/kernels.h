@@ -124,6 +124,11 @@ cudaError_t bb_descramble_launch(const uint8_t* in, uint8_t* out, const uint8_t*
 // three launches: header records, state scan, packet extraction
 cudaError_t bb_deheader_launch(const BbLaunch& p, cudaStream_t stream);
 
+// ---- mixed-MODCOD batches: gather / scatter of variable-size frames (mixed_kernel.cu) --------------------
+cudaError_t gather_launch(const uint8_t* src, const unsigned long long* off, uint8_t* dst, int bytes, int frames, cudaStream_t stream);
+cudaError_t scatter_launch(const uint8_t* src, const unsigned long long* off, uint8_t* dst, int bytes, int frames, const int32_t* v0,
+                           const int32_t* v1, const int32_t* pos, int32_t* o0, int32_t* o1, cudaStream_t stream);
+
 // one-thread kernel that publishes `value` at *flag (stream-ordered after the copies before it)
 cudaError_t flag_launch(unsigned int* flag, unsigned int value, cudaStream_t stream);
 

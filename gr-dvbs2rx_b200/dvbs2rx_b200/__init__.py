@@ -75,6 +75,11 @@ _SIGS = {
     "dvbs2b200_demap_dev": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, _P]),
     "dvbs2b200_fec_decode": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "dvbs2b200_fec_decode_dev": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "dvbs2b200_mixed_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, _P, _P, _P]),
+    "dvbs2b200_mixed_destroy": (None, [_P]),
+    "dvbs2b200_mixed_code_info": (C.c_int, [_P, C.c_int, C.POINTER(CodeInfo)]),
+    "dvbs2b200_mixed_fec_decode": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
+    "dvbs2b200_mixed_launch_count": (C.c_uint64, [_P]),
     "dvbs2b200_estimate_snr": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P]),
     "dvbs2b200_estimate_snr_dev": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, _P]),
     "dvbs2b200_bb_descramble": (C.c_int, [_P, _P, C.c_int, _P]),
@@ -362,3 +367,57 @@ class Code:
                        d_corr, stream):
         _check(lib().dvbs2b200_fec_decode_dev(self._h, constellation, d_iq, d_n0, d_llr, frames, max_trials,
                                               term_group, d_msg, d_trials, d_corr, stream))
+
+
+class MixedCodes:
+    """A set of MODCODs on one device for mixed (VCM/ACM) batches: frames carry a per-frame code id."""
+
+    def __init__(self, modcods, device=0):
+        """modcods: [(standard, framesize, rate), ...]"""
+        self._h = _P()
+        n = len(modcods)
+        std = (C.c_int * n)(*[m[0] for m in modcods])
+        fs = (C.c_int * n)(*[m[1] for m in modcods])
+        rt = (C.c_int * n)(*[m[2] for m in modcods])
+        _check(lib().dvbs2b200_mixed_create(C.byref(self._h), device, n, std, fs, rt))
+        self.infos = []
+        for c in range(n):
+            info = CodeInfo()
+            _check(lib().dvbs2b200_mixed_code_info(self._h, c, C.byref(info)))
+            self.infos.append(info)
+
+    def close(self):
+        if self._h:
+            lib().dvbs2b200_mixed_destroy(self._h)
+            self._h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(lib().dvbs2b200_mixed_launch_count(self._h))
+
+    def sizes(self, code_id):
+        """(input bytes, output bytes) per frame of a batch."""
+        n = np.array([i.n_ldpc for i in self.infos], dtype=np.int64)[code_id]
+        k = np.array([i.kbch // 8 for i in self.infos], dtype=np.int64)[code_id]
+        return n, k
+
+    def fec_decode(self, code_id, llr, max_trials=25):
+        """code_id [F] uint8; llr: the frames' int8 LLRs back to back.  Returns (msg bytes back to back,
+        trials_left [F], corrections [F])."""
+        code_id = _np(code_id, np.uint8)
+        F = code_id.size
+        n, k = self.sizes(code_id)
+        llr = _np(llr, np.int8).ravel()
+        assert llr.size == int(n.sum())
+        msg = np.empty(int(k.sum()), dtype=np.uint8)
+        trials = np.empty(F, dtype=np.int32)
+        corr = np.empty(F, dtype=np.int32)
+        _check(lib().dvbs2b200_mixed_fec_decode(self._h, F, code_id.ctypes.data, llr.ctypes.data, max_trials, msg.ctypes.data,
+                                                trials.ctypes.data, corr.ctypes.data))
+        return msg, trials, corr

@@ -58,3 +58,14 @@ def make_code(standard, framesize, rate, local_device):
     dev = torch.device("cuda", local_device)
     blob = broadcast_tables(lambda: build_tables_host(standard, framesize, rate), dev)
     return Code(device=local_device, tables=np.ascontiguousarray(blob.numpy()))
+
+
+def shard_mixed(frame_in_bytes, frame_out_bytes, rank, world):
+    """Contiguous shard of a mixed-MODCOD batch: frames [lo, hi) and the byte ranges of their input and
+    output in the back-to-back buffers.  Frames are split by count (they are independent); the byte
+    offsets follow from the per-frame sizes."""
+    n = len(frame_in_bytes)
+    lo, hi = shard_range(n, rank, world, multiple=1)
+    cin = np.concatenate([[0], np.cumsum(np.asarray(frame_in_bytes, dtype=np.int64))])
+    cout = np.concatenate([[0], np.cumsum(np.asarray(frame_out_bytes, dtype=np.int64))])
+    return (lo, hi), (int(cin[lo]), int(cin[hi])), (int(cout[lo]), int(cout[hi]))

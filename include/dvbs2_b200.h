@@ -143,6 +143,25 @@ int dvbs2b200_demap(dvbs2b200_code* h, int constellation, const float* iq, int f
 int dvbs2b200_demap_dev(dvbs2b200_code* h, int constellation, const float* d_iq, int frames,
                         const float* d_n0, int8_t* d_llr, void* stream);
 
+/* ---- mixed-MODCOD (VCM/ACM) batches ------------------------------------------------------------ */
+/* The reference's blocks are CCM: one MODCOD per block instance (lib/ldpc_decoder_bb_impl.cc:79-368), a VCM
+ * receiver runs one chain per MODCOD.  A dvbs2b200_mixed holds one code handle per MODCOD of the stream on
+ * one device and decodes a batch whose frames carry a per-frame code id (BASELINE config 5): the frames are
+ * bucketed by code, each bucket runs through that code's LDPC + BCH kernels on its own stream (buckets
+ * overlap on the device), results return to the frames' positions.
+ *   code_id [frames]  index into the set given to dvbs2b200_mixed_create
+ *   llr     the frames' soft input back to back, n_ldpc(code_id[f]) bytes each
+ *   msg     the BBFRAMEs back to back, kbch(code_id[f])/8 bytes each
+ * Per-frame termination (term_group 0).  Results are those of dvbs2b200_fec_decode on each code's frames. */
+typedef struct dvbs2b200_mixed dvbs2b200_mixed;
+int dvbs2b200_mixed_create(dvbs2b200_mixed** m, int device, int n_codes, const int* standard, const int* framesize,
+                           const int* rate);
+void dvbs2b200_mixed_destroy(dvbs2b200_mixed* m);
+int dvbs2b200_mixed_code_info(const dvbs2b200_mixed* m, int code, dvbs2b200_code_info* info);
+int dvbs2b200_mixed_fec_decode(dvbs2b200_mixed* m, int frames, const uint8_t* code_id, const int8_t* llr,
+                               int max_trials, uint8_t* msg, int32_t* trials_left, int32_t* corrections);
+uint64_t dvbs2b200_mixed_launch_count(const dvbs2b200_mixed* m);
+
 /* ---- SNR estimate of the demapper block ------------------------------------------------------- */
 /* dvbs2b200_estimate_snr <- the initial estimate in general_work  lib/xfecframe_demapper_cb_impl.cc:123-146
  *                           (QpskConstellation::estimate_snr      lib/qpsk.h:240-244, PSK hard/map lib/psk.hh:135-157)

@@ -203,3 +203,36 @@ def test_snr_estimate_matches_oracle(gpu, oracle):
         code.close()
     with pytest.raises(d.Dvbs2Error):
         d.Code(0, 1, d.C1_2).estimate_snr(d.MOD_16APSK, np.zeros((1, 16200, 2), np.float32))
+
+
+def test_mixed_modcod_batch_matches_per_code_oracle(gpu, oracle):
+    """BASELINE config 5: frames of five MODCODs interleaved in one batch, per-frame code id.  The result of
+    every frame equals the single-code oracle run on that frame (oracle = per-code runs re-assembled)."""
+    d = gpu
+    from dvbs2rx_b200 import vectors
+    modcods = [(0, 1, d.C1_2, 2.0), (0, 1, d.C3_4, 4.6), (0, 1, d.C3_5, 3.5), (0, 0, d.C2_3, 4.2), (0, 1, d.C9_10, 6.6)]
+    mixed = d.MixedCodes([m[:3] for m in modcods])
+    rng = np.random.default_rng(51)
+    per_code = {}
+    for c, (std, fs, rate, esn0) in enumerate(modcods):
+        msg, cw, llr, info = vectors.make_llr_frames(std, fs, rate, 3 if fs else 6, esn0, seed=60 + c)
+        per_code[c] = dict(msg=msg, llr=llr, info=info, fs=fs, next=0)
+    order = np.concatenate([np.full(per_code[c]["llr"].shape[0], c, dtype=np.uint8) for c in per_code])
+    rng.shuffle(order)
+    llr_cat, want_msg, want_tr, want_co = [], [], [], []
+    for c in order:
+        pc = per_code[int(c)]
+        i = pc["next"]
+        pc["next"] += 1
+        llr_cat.append(pc["llr"][i])
+        info = pc["info"]
+        o_post, o_ret = oracle.ldpc_decode(info.table, pc["llr"][i:i + 1], 25)
+        o_msg, o_corr = oracle.bch_decode(oracle.bch(pc["fs"], info.t, info.nbch), oracle.pack_hard(o_post, info.nbch))
+        want_msg.append(o_msg[0])
+        want_tr.append(o_ret[0])
+        want_co.append(o_corr[0])
+    msg, tr, co = mixed.fec_decode(order, np.concatenate(llr_cat), 25)
+    assert np.array_equal(msg, np.concatenate(want_msg))
+    assert np.array_equal(tr, np.array(want_tr)) and np.array_equal(co, np.array(want_co))
+    assert (tr >= 0).sum() >= len(order) - 2  # nearly everything converges at these SNRs
+    mixed.close()

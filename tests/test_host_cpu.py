@@ -160,3 +160,19 @@ def test_split_schedule_covers_every_table(built):
             os.environ.pop("DVBS2B200_SPLIT", None)
         else:
             os.environ["DVBS2B200_SPLIT"] = old
+
+
+def test_mixed_batch_sharding(built):
+    """Mixed-MODCOD batches shard by frame count; byte ranges follow the per-frame sizes and tile the buffers."""
+    from dvbs2rx_b200 import sharding
+    rng = np.random.default_rng(2)
+    sizes_in = rng.choice([16200, 64800], size=37)
+    sizes_out = np.where(sizes_in == 16200, 1323, 4026)
+    for world in (1, 2, 3, 8):
+        prev_hi, prev_in, prev_out = 0, 0, 0
+        for r in range(world):
+            (lo, hi), (i0, i1), (o0, o1) = sharding.shard_mixed(sizes_in, sizes_out, r, world)
+            assert lo == prev_hi and i0 == prev_in and o0 == prev_out
+            assert i1 - i0 == sizes_in[lo:hi].sum() and o1 - o0 == sizes_out[lo:hi].sum()
+            prev_hi, prev_in, prev_out = hi, i1, o1
+        assert prev_hi == 37 and prev_in == sizes_in.sum() and prev_out == sizes_out.sum()
