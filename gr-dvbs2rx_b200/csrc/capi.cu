@@ -151,7 +151,7 @@ int create_from_blob(dvbs2b200_code** out, int device, std::vector<uint8_t>&& bl
         return bail(cuda_fail(e, "cudaMalloc(tables)"));
     if ((e = cudaMemcpy(h->d_blob, h->blob.data(), h->blob.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
         return bail(cuda_fail(e, "cudaMemcpy(tables)"));
-    h->ldpc_smem = ldpc_smem_bytes(h->hdr.N, h->hdr.smem_bytes, nullptr);
+    h->ldpc_smem = ldpc_smem_bytes(h->hdr.N, h->hdr.smem_bytes, h->hdr.chain_scratch != 0, nullptr);
     auto ctas_per_sm = h->hdr.split_steps ? ldpc_ctas_per_sm_split : ldpc_ctas_per_sm_wavefront;
     if (h->hdr.max_cnt <= 28 && h->ldpc_smem <= (size_t)h->smem_optin)
         h->ldpc_ctas = ctas_per_sm(h->hdr.max_cnt, h->hdr.uniform_cnt != 0, false, h->ldpc_smem);
@@ -236,7 +236,7 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
     p.tab = h->d_blob + hd.smem_off;
     p.tab_bytes = hd.smem_bytes;
     p.work = reinterpret_cast<const uint16_t*>(h->d_blob + hd.order_off);
-    size_t smem = ldpc_smem_bytes(hd.N, hd.smem_bytes, &p);
+    size_t smem = ldpc_smem_bytes(hd.N, hd.smem_bytes, hd.chain_scratch != 0, &p);
     const int group = term_group > 1 ? term_group : 0;
     // wavefront state in tensor memory: per-frame mode only (the cooperative launch of the group mode is
     // sized by the occupancy calculator, which does not co-schedule kernels that use TMEM)
@@ -495,6 +495,8 @@ int bb_deheader_dev(dvbs2b200_code* h, const uint8_t* d_bb, int frames, int scra
     }
     if (!d_bb || !d_ts)
         return fail(DVBS2B200_EINVAL, "null buffer");
+    if ((uintptr_t)d_ts & 3)
+        return fail(DVBS2B200_EINVAL, "ts buffer must be 4-byte aligned");
     if ((rc = h->d_bbrec.ensure((size_t)frames * sizeof(uint32_t))) || (rc = h->d_bbplan.ensure((size_t)frames * sizeof(BbPlan))))
         return rc;
     BbLaunch p;

@@ -37,10 +37,11 @@ const ModcodDef* find_modcod(int standard, int framesize, int rate)
 // such layers we compute level[j] = 1 + max(level[j'] : j' < j touches one of j's bits); check
 // nodes of equal level are independent, and running the levels in order reproduces the serial
 // result bit for bit.
-// Which form of the conflict layers is faster was measured per code on B200 (profiles/): split steps win
-// where a good part of the layers is order sensitive and their shared links are few (DVB-S2 3/4, 2/3 short:
-// +16..18 %), the wavefront form (tensor-memory state, warp-0 runs) where conflict layers are rare (1/2 normal)
-// or carry many shared links on high-degree check nodes (9/10 normal).
+// Which form of the conflict layers is faster was measured per code on B200 (profiles/r01b_sweep_*.jsonl).
+// Split steps win wherever the conflict layers carry one doubled group (the chain form: DVB-S2 1/2, 3/5, 3/4
+// normal, 2/3 short: +3 .. +40 %); layers with several doubled groups or a tripled one fall back to the
+// level-by-level form, and when those dominate on high-degree check nodes (9/10 normal: 13 of 18 layers) the
+// wavefront form with link-parallel runs stays ahead.
 bool choose_split(const LdpcTableDef& def)
 {
     if (const char* env = getenv("DVBS2B200_SPLIT"))
@@ -48,17 +49,16 @@ bool choose_split(const LdpcTableDef& def)
     std::vector<std::vector<int>> groups(def.q);
     for (int c = 0; c < def.n_circ; ++c)
         groups[def.circ[c] >> 17].push_back((int)((def.circ[c] >> 9) & 0xff));
-    int conflict_layers = 0, max_shared = 0;
+    int multi = 0; // conflict layers that cannot take the chain form
     for (auto& g : groups) {
         std::sort(g.begin(), g.end());
         int shared = 0;
         for (size_t a = 0; a < g.size(); ++a)
             if ((a && g[a] == g[a - 1]) || (a + 1 < g.size() && g[a] == g[a + 1]))
                 ++shared;
-        conflict_layers += shared > 0;
-        max_shared = std::max(max_shared, shared);
+        multi += shared > 2;
     }
-    return max_shared <= 4 && 7 * conflict_layers >= 3 * def.q;
+    return 3 * multi <= def.q;
 }
 
 void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem, int split_arg)
@@ -75,6 +75,8 @@ void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem, int spl
     std::vector<int> last(ngroups * 360);
     const bool split = split_arg < 0 ? choose_split(def) : split_arg != 0;
     s.split = split;
+    const char* env_chain = getenv("DVBS2B200_CHAIN"); // diagnostics: 0 = level-by-level form for every split step
+    const bool chain = !(env_chain && atoi(env_chain) == 0);
     for (int i = 0; i < q; ++i) {
         auto& circ = per_layer[i];
         LayerRec& L = s.layers[i];
@@ -141,6 +143,21 @@ void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem, int spl
             s.order.push_back(0);
             for (int lv = 1; lv <= depth; ++lv)
                 s.order.push_back((uint16_t)(32 * __builtin_popcount(warps[lv - 1] | warps[lv])));
+            // Chain form (code_tables.h): exactly two circulants (shifts a0 < a1) in one group.  With d = a1 - a0,
+            // the bit node j reaches through link 0 is the bit node (j + d) mod 360 reaches through link 1, so
+            // with delta = min(d, 360 - d) the layer is `delta` independent chains j, j + delta, j + 2 delta, ...
+            // along which the updated bit is handed from a node's "out" link to the next node's "in" link.
+            if (n_shared == 2 && chain) {
+                const int a0 = circ[circ.size() - 2].second, a1 = circ[circ.size() - 1].second;
+                const int d = ((a1 - a0) % 360 + 360) % 360;
+                const int delta = std::min(d, 360 - d);
+                const int out_link = d <= 180 ? 0 : 1; // which of the two shared links carries the bit forward
+                if (delta >= 1 && (360 + delta - 1) / delta == depth) {
+                    st.work_off |= kStepChain | (out_link ? kStepChainOutLink1 : 0u);
+                    st.run_len = (uint8_t)delta; // <= 180
+                    s.has_chain = true;
+                }
+            }
             s.steps.push_back(st);
             continue;
         }
@@ -415,6 +432,7 @@ bool build_blob(int standard, int framesize, int rate, std::vector<uint8_t>& blo
     h.uniform_cnt = (s.min_cnt == s.max_cnt) ? 1 : 0;
     h.bch_shorten = ((1u << h.gf_m) - 1) - (uint32_t)mc->nbch;
     h.split_steps = s.split ? 1u : 0u;
+    h.chain_scratch = s.has_chain ? 1u : 0u;
 
     size_t off = sizeof(BlobHeader);
     h.smem_off = (uint32_t)off;

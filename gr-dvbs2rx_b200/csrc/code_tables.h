@@ -29,7 +29,7 @@ const ModcodDef* find_modcod(int standard, int framesize, int rate);
 
 // ---- packed blob ---------------------------------------------------------------------------
 constexpr uint32_t kBlobMagic = 0x32425344u; // "DSB2"
-constexpr uint32_t kBlobVersion = 10;
+constexpr uint32_t kBlobVersion = 12;
 
 // One per layer, 8 bytes, lives in shared memory.
 struct LayerRec {
@@ -67,6 +67,9 @@ constexpr uint32_t kStepRun = 1u << 25;          // part of a run executed by a 
 constexpr uint32_t kStepWarpsShift = 26;         // 3 bits: warps taking part in the run
 constexpr uint32_t kStepLinkParallel = 1u << 29; // run class: link parallel (else one node per lane)
 constexpr uint32_t kStepSplit = 1u << 30;        // whole conflict layer in one step, see below
+constexpr uint32_t kStepChain = 1u << 31;        // split step whose shared links form independent chains (below);
+                                                 // StepRec::run_len = delta, kStepChainOutLink1 = forwarding link
+constexpr uint32_t kStepChainOutLink1 = 1u << 29; // (shares its bit with kStepLinkParallel: never both)
 constexpr uint32_t kStepOffMask = (1u << 24) - 1;
 // Split step (the default for conflict layers).  Only the links into a 360-bit group that carries two
 // or more circulants of the layer ("shared" links, LayerRec::conflict of them, sorted last) are order
@@ -76,6 +79,11 @@ constexpr uint32_t kStepOffMask = (1u << 24) - 1;
 // shared links into its partial minima / sign product and updates those bits, then the private links
 // are updated in s16x2 again.  The dependent chain through a layer shrinks from a whole check-node
 // update per level to a 2-link merge; StepRec::count = depth, work[] holds level[j] (1-based).
+// Chain form of a split step (one doubled group, the usual case): the serial order through the layer is
+// `delta` independent chains of nodes j, j + delta, ...; one lane walks one chain and hands the updated bit
+// to the next node in a register, so the dependent path per node is a 2-link merge with no barrier and no
+// shared-memory round trip.  The nodes' partial results travel through a 360 x 8-byte scratch in shared
+// memory.  delta and the forwarding link ride in the step record.
 constexpr int kMaxSharedLinks = 12; // largest over the 57 tables (DVB-S2 8/9 short)
 
 // Tensor memory as scratch for the check-node state of order-sensitive layers.  Those layers are a
@@ -105,7 +113,8 @@ struct BlobHeader {
     uint32_t antilog_off, log_off; // uint16[2^m] each: alpha^i (i < 2^m-1), log(x)
     uint32_t bch_shorten;          // s = 2^m - 1 - nbch
     uint32_t split_steps;          // 1: conflict layers are split steps (kernels of the _split build), 0: wavefront steps
-    uint32_t reserved1[2];
+    uint32_t chain_scratch;        // 1: some split step is in chain form: the kernel needs the 360 x 8 B node scratch
+    uint32_t reserved1[1];
 };
 static_assert(sizeof(BlobHeader) % 16 == 0, "header must keep sections 16-byte aligned");
 
@@ -139,7 +148,8 @@ struct Schedule {
     std::vector<uint16_t> order; // work[]: check-node indices of the conflict steps
     std::vector<uint8_t> tcol;   // per step: first TMEM column of its state, or kNoTmem
     int max_cnt = 0, min_cnt = 1 << 30, steps_per_iter = 0, max_depth = 0, conflict_layers = 0, barriers_per_iter = 0;
-    bool split = false; // conflict layers emitted as split steps
+    bool split = false;     // conflict layers emitted as split steps
+    bool has_chain = false; // at least one of them in chain form
 };
 // split: 1 / 0 force the form of the conflict layers, -1 lets choose_split() decide (env DVBS2B200_SPLIT overrides)
 void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem = true, int split = -1);

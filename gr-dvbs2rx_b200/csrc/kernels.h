@@ -15,7 +15,7 @@ struct LdpcLaunch {
     uint32_t tab_bytes;   // multiple of 16
     const uint16_t* work; // check-node lists of the conflict steps
     // shared-memory carve-up (bytes from the start of dynamic shared memory)
-    uint32_t smem_tab_off, smem_bar_off;
+    uint32_t smem_tab_off, smem_bar_off, smem_rec_off; // rec: 360 x 8 B node scratch of chain-form split steps (0: none)
     // per-CTA check-node state, [grid][R * words] uint32, L2 resident
     uint32_t* msg_scratch;
     // batch
@@ -41,7 +41,7 @@ struct LdpcLaunch {
 };
 
 // fills the smem_* offsets of p (if non-null) and returns the dynamic shared memory size
-size_t ldpc_smem_bytes(int N, uint32_t tab_bytes, LdpcLaunch* p);
+size_t ldpc_smem_bytes(int N, uint32_t tab_bytes, bool chain_scratch, LdpcLaunch* p);
 // Two builds of ldpc_kernel.cu: order-sensitive layers as split steps (_split) or as wavefront steps of whole
 // check nodes (_wavefront, with the tensor-memory state variant `tmem`); the blob says which schedule it holds.
 cudaError_t ldpc_launch_split(const LdpcLaunch& p, int max_cnt, bool uniform, bool tmem, int grid, size_t smem, cudaStream_t stream);

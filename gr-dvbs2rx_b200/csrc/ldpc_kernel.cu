@@ -560,18 +560,110 @@ __device__ __noinline__ void split_levels(const SplitCtx<WIDE>* cp, uint32_t* io
     io[0] = k0, io[1] = k1, io[2] = sx, io[3] = shs_lo, io[4] = shs_hi;
 }
 
+// ---- chain form of phase 2 (code_tables.h) ------------------------------------------------------------
+// Node record in the shared-memory scratch, written by phase 1 and rewritten by the walk:
+//   x: partial k0 (low half) | partial k1 (high half) -> final k0 | k1
+//   y: bit 0 sign of the partial sign product, bits 1..6 old message of shared link 0 (+32), bits 7..12 of link 1
+//      -> bit 0 final sign product, bit 1 / 2 sign of the new message on shared link 0 / 1
+__device__ __forceinline__ int chain_operand_addr(const uint2 e, int j)
+{
+    const int ap = (int)(e.x >> 16), ra = (int)(e.y & 1u);
+    const int gbase = (int)(e.x & 0xffffu) - 360 + 2 * ap;
+    int s = j - ap - kPairs * ra; // (j - shift) mod 360
+    s += (s < 0) ? 360 : 0;
+    return data_addr(gbase, s);
+}
+
+// Lane c < delta walks the chain c, c + delta, ...  The bit that a node updates through its "out" link is the
+// bit the next node reads through its "in" link: it travels in a register.  A chain's last node meets, through
+// its out link, the bit that the first node of some chain updated through its in link at step 0 -- hence one
+// barrier among the walking warps after step 0, and none after that.
+__device__ __noinline__ void split_chain_walk(int8_t* __restrict__ L, uint2* __restrict__ rec, const uint2 e_in, const uint2 e_out,
+                                              int d_in, int d_out, int in_is_link1, int delta, int tid)
+{
+    // called by every lane of the first ceil(delta / 32) warps (the barrier below is warp granular)
+    const int nwarps = (delta + 31) >> 5;
+    const bool live = tid < delta;
+    // what a node needs that does not depend on its predecessor: fetched one node ahead
+    struct Pre {
+        uint2 r;
+        int a_in, a_out, l_out;
+    };
+    auto fetch = [&](int j) {
+        Pre q;
+        q.r = rec[j];
+        q.a_in = chain_operand_addr(e_in, j);
+        q.a_out = chain_operand_addr(e_out, j);
+        q.l_out = (int)L[q.a_out];
+        return q;
+    };
+    // the node itself; returns the updated bit of its out link
+    auto node = [&](int j, const Pre& q, int l_in) {
+        const uint2 r = q.r;
+        const int old0 = (int)((r.y >> 1) & 63u) - 32, old1 = (int)((r.y >> 7) & 63u) - 32;
+        const int old_in = in_is_link1 ? old1 : old0, old_out = in_is_link1 ? old0 : old1;
+        const int x_in = min(max(l_in - old_in, -128), 127), x_out = min(max(q.l_out - old_out, -128), 127);
+        const int mg_in = max(min(abs(x_in), 127) - 1, 0), mg_out = max(min(abs(x_out), 127) - 1, 0);
+        int k0h = (int)(r.x & 0xffffu), k1h = (int)(r.x >> 16);
+        const int key_in = mg_in * 32 + d_in, key_out = mg_out * 32 + d_out;
+        // the out link does not depend on the predecessor: merged first, the in link last
+        k1h = min(k1h, max(k0h, key_out));
+        k0h = min(k0h, key_out);
+        k1h = min(k1h, max(k0h, key_in));
+        k0h = min(k0h, key_in);
+        const int min0 = k0h >> 5, min1 = k1h >> 5;
+        const int sgn = (int)(r.y & 1u) ^ (x_in < 0) ^ (x_out < 0); // 1: the product of all signs is negative
+        const int m_in = min0 + min1 - min(mg_in, min1), m_out = min0 + min1 - min(mg_out, min1);
+        const int neg_in = sgn ^ (x_in < 0), neg_out = sgn ^ (x_out < 0);
+        const int nl_in = min(max(x_in + (neg_in ? -m_in : m_in), -128), 127);
+        const int nl_out = min(max(x_out + (neg_out ? -m_out : m_out), -128), 127);
+        L[q.a_in] = (int8_t)nl_in;
+        if (j + delta >= 360)
+            L[q.a_out] = (int8_t)nl_out; // end of the chain: nobody takes the bit over
+        const int s0 = in_is_link1 ? neg_out : neg_in, s1 = in_is_link1 ? neg_in : neg_out;
+        rec[j] = make_uint2((uint32_t)k0h | ((uint32_t)k1h << 16), (uint32_t)sgn | ((uint32_t)s0 << 1) | ((uint32_t)s1 << 2));
+        return nl_out;
+    };
+    int carried = 0;
+    if (live) {
+        const Pre q = fetch(tid);
+        carried = node(tid, q, (int)L[q.a_in]);
+    }
+    if (nwarps == 1)
+        __syncwarp();
+    else
+        asm volatile("bar.sync 1, %0;" ::"r"(nwarps * 32) : "memory");
+    if (live && tid + delta < 360) {
+        // (no fetch ahead across the barrier: a chain's second node may already be its last, whose out link
+        // meets a bit that a first node has just written)
+        int j = tid + delta;
+        Pre q = fetch(j);
+        for (;;) {
+            const int jn = j + delta;
+            Pre qn = q;
+            if (jn < 360)
+                qn = fetch(jn);
+            carried = node(j, q, carried);
+            if (jn >= 360)
+                break;
+            j = jn;
+            q = qn;
+        }
+    }
+}
+
 template <int CNT_MAX, bool UNIFORM, bool WIDE, bool SELF_CHECK>
 __device__ __noinline__ int process_split(int8_t* __restrict__ L, const uint2* __restrict__ edges, const LayerView lv, int layer,
                                              int p, bool active, int K, int q, uint32_t wA, uint32_t wB, uint32_t sA, uint32_t sB,
                                              uint32_t* __restrict__ msg_out, uint64_t pol, int depth, const uint16_t* __restrict__ level_tab,
-                                             volatile int* progress, unsigned long long* prof = nullptr)
+                                             volatile int* progress, unsigned long long* prof, uint2* __restrict__ rec, bool chain, int chain_delta, int chain_out_link)
 {
     constexpr int DEG_MAX = CNT_MAX + 2;
     const bool first = (layer == 0 && p == 0);
     const int half = kPairs * q;
     const int npriv = lv.cnt - lv.nshared; // private data links: d - 2 < npriv
     int lvA = 0, lvB = 0;
-    if (active) {
+    if (active && !chain) {
         lvA = (int)__ldg(level_tab + p);
         lvB = (int)__ldg(level_tab + p + kPairs);
     }
@@ -651,7 +743,72 @@ __device__ __noinline__ int process_split(int8_t* __restrict__ L, const uint2* _
     // they arrive, or sync if they also have nodes in level l) and in level l (they sync); the host
     // precomputed the thread count of each barrier (level_tab[360 + l]).
     uint32_t shs_lo = 0, shs_hi = 0; // new sign bits of the shared links, same layout as newsg_lo / newsg_hi
-    {
+    if (chain) {
+        // chain form: hand the nodes' partial results and old shared-link messages to the walking lanes
+        const int d0 = 2 + npriv;
+#ifdef DVBS2_PHASE_PROFILE
+        const long long tq0 = clock64();
+#endif
+        if (active) {
+#pragma unroll
+            for (int hsel = 0; hsel < 2; ++hsel) {
+                const uint32_t w = hsel ? wB : wA;
+                const uint32_t sg = WIDE ? (hsel ? sB : sA) : (w >> 17);
+                const int omin0 = (int)(w & 63u), omin1 = (int)((w >> 6) & 63u), oarg = (int)((w >> 12) & 31u);
+                uint32_t y = (sx >> (16 * hsel + 15)) & 1u;
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl) {
+                    const int d = d0 + sl;
+                    const int mc = (d == oarg) ? omin1 : omin0;
+                    const int old = ((sg >> d) & 1u) ? -mc : min(mc, 31);
+                    y |= (uint32_t)(old + 32) << (1 + 6 * sl);
+                }
+                rec[p + kPairs * hsel] = make_uint2(((k0 >> (16 * hsel)) & 0xffffu) | (((k1 >> (16 * hsel)) & 0xffffu) << 16), y);
+            }
+        }
+        __syncthreads();
+#ifdef DVBS2_PHASE_PROFILE
+        const long long tq1 = clock64();
+#endif
+        const int delta = chain_delta, out_link = chain_out_link;
+        if ((p >> 5) < ((delta + 31) >> 5)) {
+            const uint2 e0 = edges[lv.edge_begin + npriv], e1 = edges[lv.edge_begin + npriv + 1];
+            split_chain_walk(L, rec, out_link ? e0 : e1, out_link ? e1 : e0, out_link ? d0 : d0 + 1, out_link ? d0 + 1 : d0,
+                             out_link ? 0 : 1, delta, p);
+        }
+#ifdef DVBS2_PHASE_PROFILE
+        const long long tq2 = clock64();
+#endif
+        __syncthreads();
+#ifdef DVBS2_PHASE_PROFILE
+        if (prof && p == 0) {
+            const long long tq3 = clock64();
+            atomicAdd(prof + 8, (unsigned long long)(tq1 - tq0));  // records + barrier
+            atomicAdd(prof + 9, (unsigned long long)(tq2 - tq1));  // warp 0's walk
+            atomicAdd(prof + 10, (unsigned long long)(tq3 - tq2)); // waiting for the other walking warps
+            atomicAdd(prof + 11, (unsigned long long)depth);
+        }
+#endif
+        if (active) {
+#pragma unroll
+            for (int hsel = 0; hsel < 2; ++hsel) {
+                const uint2 r = rec[p + kPairs * hsel];
+                const uint32_t keep = hsel ? 0x0000ffffu : 0xffff0000u;
+                k0 = (k0 & keep) | ((r.x & 0xffffu) << (16 * hsel));
+                k1 = (k1 & keep) | ((r.x >> 16) << (16 * hsel));
+                sx = (sx & keep) | ((r.y & 1u) ? (0x8000u << (16 * hsel)) : 0u); // only the sign of sx is used from here on
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl) {
+                    const int d = d0 + sl;
+                    const uint32_t bit = ((r.y >> (1 + sl)) & 1u) << ((d & 15) + 16 * hsel);
+                    if (!WIDE || d < 16)
+                        shs_lo |= bit;
+                    else
+                        shs_hi |= bit;
+                }
+            }
+        }
+    } else {
         SplitCtx<WIDE> cx = { L, edges + lv.edge_begin + npriv, level_tab, progress, p, pkey, 2 + npriv, lv.nshared, depth, lvA, lvB,
                               active, wA, wB, sA, sB, prof };
         uint32_t io[5] = { k0, k1, sx, 0u, 0u };
@@ -1096,6 +1253,8 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
     const uint2* steps = reinterpret_cast<const uint2*>(smem + p.smem_tab_off + (size_t)p.q * 8 + (size_t)p.n_circ * 8);
     const uint8_t* tcol = smem + p.smem_tab_off + (size_t)p.q * 8 + (size_t)p.n_circ * 8 + (size_t)p.n_steps * 8;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + p.smem_bar_off);
+    uint2* const rec = reinterpret_cast<uint2*>(smem + p.smem_rec_off); // node scratch of chain-form split steps
+    (void)rec;
     __shared__ int s_group_bad;
     __shared__ uint32_t s_tmem_base;
     __shared__ int s_progress; // split steps: highest level of the current layer known to be complete
@@ -1256,7 +1415,7 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
                 const uint32_t work_off = st.y & 0x00ffffffu;
                 const bool barrier_before = (st.y >> 24) & 1u, is_run = (st.y >> 25) & 1u, link_parallel = (st.y >> 29) & 1u;
                 const int sub_warps = (int)((st.y >> 26) & 7u);
-                const bool is_split = (st.y >> 30) & 1u;
+                const bool is_split = (st.y >> 30) & 1u, is_chain = (st.y >> 31) & 1u;
                 const LayerView lv = load_layer(layers, layer);
                 const int next = s + (is_run ? run_len : 1);
                 const bool last = (next == p.n_steps);
@@ -1291,10 +1450,10 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
                     uint32_t* mo = msg + ((size_t)layer * kPairs + (tid < kPairs ? tid : 0)) * 2 * MW;
                     if (last)
                         self_bad |= process_split<CNT_MAX, UNIFORM, WIDE, true>(L, edges, lv, layer, tid, tid < kPairs, K, q, cA, cB, csA, csB, mo,
-                                                                                pol_keep, count, work + work_off, &s_progress, p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr);
+                                                                                pol_keep, count, work + work_off, &s_progress, p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr, rec, is_chain, run_len, (int)link_parallel);
                     else
                         process_split<CNT_MAX, UNIFORM, WIDE, false>(L, edges, lv, layer, tid, tid < kPairs, K, q, cA, cB, csA, csB, mo, pol_keep,
-                                                                     count, work + work_off, &s_progress, p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr);
+                                                                     count, work + work_off, &s_progress, p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr, rec, is_chain, run_len, (int)link_parallel);
                 }
 #else
                 else if (is_run) {
@@ -1470,7 +1629,7 @@ cudaError_t flag_launch(unsigned int* flag, unsigned int value, cudaStream_t str
     return cudaGetLastError();
 }
 
-size_t ldpc_smem_bytes(int N, uint32_t tab_bytes, LdpcLaunch* p)
+size_t ldpc_smem_bytes(int N, uint32_t tab_bytes, bool chain_scratch, LdpcLaunch* p)
 {
     size_t off = ((size_t)N + 15) & ~(size_t)15;
     if (p)
@@ -1480,6 +1639,10 @@ size_t ldpc_smem_bytes(int N, uint32_t tab_bytes, LdpcLaunch* p)
     if (p)
         p->smem_bar_off = (uint32_t)off;
     off += 16;
+    if (p)
+        p->smem_rec_off = chain_scratch ? (uint32_t)off : 0u;
+    if (chain_scratch)
+        off += 360 * 8;
     return off;
 }
 

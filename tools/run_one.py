@@ -1,0 +1,105 @@
+#!/usr/bin/env python3
+"""One pass of a chosen piece of the path over a synthetic batch, for profiling under ncu on the GPU box:
+
+    python tools/run_one.py fec   C3_4 1 4.6 50 2664     # LDPC + BCH (device-resident input)
+    python tools/run_one.py ts    C1_2 1 2.0 25 2664     # LDPC + BCH + descrambler + deheader -> TS packets
+    python tools/run_one.py bb    C1_2 1 0 0 8192        # descrambler + deheader alone on clean BBFRAMEs
+    python tools/run_one.py snr   C3_5 1 6.2 0 2664      # SNR estimate (8PSK for 3/5, else QPSK) + demap
+
+Prints device time per pass (CUDA events) and the derived rates; not the bench line."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "gr-dvbs2rx_b200"))
+import dvbs2rx_b200 as d  # noqa: E402
+from dvbs2rx_b200 import bbframes as bbf, vectors  # noqa: E402
+
+what, rate_name = sys.argv[1], sys.argv[2]
+fs, esn0, trials, F = int(sys.argv[3]), float(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])
+rate = d.RATE[rate_name]
+code = d.Code(0, fs, rate)
+info = code.info
+dev = torch.device("cuda", 0)
+stream = torch.cuda.current_stream().cuda_stream
+rng = np.random.default_rng(1)
+kb = info.kbch // 8
+
+
+def timed(fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps * 1e-3
+
+
+def bb_stream(n):
+    up = bbf.ts_packets((n * (kb - 10) + 187) // 188 + 1, rng)
+    return up, bbf.bbframe_stream(info.kbch, n, up)
+
+
+if what in ("fec", "ts"):
+    base = 64
+    up, bb = bb_stream(base)
+    msg_bits = vectors.unpack_bits(bbf.scramble(bb), info.kbch)
+    cw = vectors.ldpc_encode_bits(info.table, vectors.bch_encode_bits(msg_bits, fs, info.t, info.nbch)[:, :info.k_ldpc])
+    iq, n0 = vectors.awgn(vectors.map_symbols(cw, d.MOD_QPSK, rate), esn0, rng)
+    llr = np.tile(vectors.qpsk_llr(iq, n0), (F // base + 1, 1))[:F]
+    d_llr = torch.from_numpy(llr).to(dev)
+    d_tr = torch.empty(F, dtype=torch.int32, device=dev)
+    d_co = torch.empty(F, dtype=torch.int32, device=dev)
+    if what == "fec":
+        d_msg = torch.empty((F, kb), dtype=torch.uint8, device=dev)
+        t = timed(lambda: code.fec_decode_dev(0, None, None, d_llr.data_ptr(), F, trials, 0, d_msg.data_ptr(), d_tr.data_ptr(),
+                                              d_co.data_ptr(), stream))
+        print("fec %s: %.3f ms, %.0f frames/s, mean iterations %.1f" % (
+            rate_name, t * 1e3, F / t, float(np.where(d_tr.cpu().numpy() >= 0, trials - d_tr.cpu().numpy(), trials).mean())))
+    else:
+        cap = code.bb_ts_capacity(F)
+        d_ts = torch.empty(cap, dtype=torch.uint8, device=dev)
+
+        def run():
+            code.bb_reset()
+            code.fec_decode_ts_dev(0, None, None, d_llr.data_ptr(), F, trials, 0, d_ts.data_ptr(), cap, d_tr.data_ptr(), d_co.data_ptr(), stream)
+        t = timed(run)
+        print("ts %s: %.3f ms, %.0f frames/s, %d TS bytes, counters %s" % (rate_name, t * 1e3, F / t, code.bb_produced_dev(stream),
+                                                                        code.bb_counters()))
+elif what == "bb":
+    up, bb = bb_stream(F)
+    d_bb = torch.from_numpy(bbf.scramble(bb)).to(dev)
+    cap = code.bb_ts_capacity(F)
+    d_ts = torch.empty(cap, dtype=torch.uint8, device=dev)
+
+    def run():
+        code.bb_reset()
+        code.bb_deheader_dev(d_bb.data_ptr(), F, 1, d_ts.data_ptr(), cap, stream)
+    t = timed(run, reps=10)
+    n = code.bb_produced_dev(stream)
+    ok = np.array_equal(d_ts[:n].cpu().numpy(), up[:n // 188].ravel())
+    print("bb %s: %.1f us per call of %d BBFRAMEs, %.1f GB/s (read kbch/8 + write TS), packets ok %s" % (
+        rate_name, t * 1e6, F, (F * kb + n) / t / 1e9, ok))
+elif what == "snr":
+    mod = d.MOD_8PSK if rate_name == "C3_5" else d.MOD_QPSK
+    msg, cw, info2 = vectors.encode_frames(0, fs, rate, 16, rng)
+    iq, n0 = vectors.awgn(vectors.map_symbols(cw, mod, rate), esn0, rng)
+    iq = np.tile(iq, (F // 16 + 1, 1, 1))[:F]
+    d_iq = torch.from_numpy(iq).to(dev)
+    d_snr = torch.empty(F, dtype=torch.float32, device=dev)
+    d_n0 = torch.full((F,), float(n0), dtype=torch.float32, device=dev)
+    d_llr = torch.empty((F, info.n_ldpc), dtype=torch.int8, device=dev)
+    t1 = timed(lambda: code.estimate_snr_dev(mod, d_iq.data_ptr(), None, F, d_snr.data_ptr(), stream), reps=10)
+    t2 = timed(lambda: code.demap_dev(mod, d_iq.data_ptr(), F, d_n0.data_ptr(), d_llr.data_ptr(), stream), reps=10)
+    t3 = timed(lambda: code.estimate_snr_dev(mod, d_iq.data_ptr(), d_llr.data_ptr(), F, d_snr.data_ptr(), stream), reps=10)
+    bits = d.bits_per_symbol(mod)
+    iq_bytes = F * (info.n_ldpc // bits) * 8
+    print("snr %s: symbols-only %.1f us (%.0f GB/s), demap %.1f us (%.0f GB/s), with LLR %.1f us (%.0f GB/s); mean %.2f dB" % (
+        rate_name, t1 * 1e6, iq_bytes / t1 / 1e9, t2 * 1e6, (iq_bytes + F * info.n_ldpc) / t2 / 1e9, t3 * 1e6,
+        (iq_bytes + F * info.n_ldpc) / t3 / 1e9, float(10 * np.log10(d_snr.cpu().numpy().mean()))))
