@@ -63,7 +63,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def window(self, t0, t1):
+        """Keep only the samples taken while the GPU was under load ([t0, t1] in perf_counter time)."""
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if not self.proc:
@@ -76,7 +80,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
+        lines = [l for t, l in self.samples if t0 is None or t0 <= t <= t1] or [l for _, l in self.samples[-3:]]
+        for s in lines:
             parts = [p.strip() for p in s.split(",")]
             if len(parts) < 7:
                 continue
@@ -210,22 +216,22 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # nvidia-smi takes a moment to come up: started ahead of the warm-up, windowed below
     for _ in range(max(args.warmup, 3)):
         step()
     sync_all()
     launches0 = code.launches
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    t_load0 = time.perf_counter()
     t_start.record()
     for k in range(args.steps):
         step(evs[k])
     t_end.record()
     sync_all()
-    clocks = sampler.stop() if rank == 0 else None
     launches = code.launches - launches0
     elapsed_ms = t_start.elapsed_time(t_end)
     ldpc_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
@@ -256,6 +262,9 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(e2, op=dist.ReduceOp.MAX)
     e2e_value = world * F * e2e_steps / float(e2.item())
+    # clocks / throttle reasons sampled while the GPU was busy: the timed region and the end-to-end loop after it
+    sampler.window(t_load0, time.perf_counter())
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
         peak, peak_kind = load_peaks()
