@@ -157,6 +157,8 @@ int create_from_blob(dvbs2b200_code** out, int device, std::vector<uint8_t>&& bl
         h->ldpc_ctas = ctas_per_sm(h->hdr.max_cnt, h->hdr.uniform_cnt != 0, false, h->ldpc_smem);
     if (h->ldpc_ctas > 0 && h->hdr.tmem_cols > 0 && !h->hdr.split_steps)
         h->ldpc_ctas_tmem = ctas_per_sm(h->hdr.max_cnt, h->hdr.uniform_cnt != 0, true, h->ldpc_smem);
+    if (h->hdr.split_steps && h->hdr.level_calls && h->hdr.max_cnt <= 13) // the split build's other kernel variant
+        h->ldpc_ctas = ctas_per_sm(h->hdr.max_cnt, h->hdr.uniform_cnt != 0, true, h->ldpc_smem);
     if (getenv("DVBS2B200_DEBUG"))
         fprintf(stderr, "[dvbs2b200] table %d: %s steps, ldpc smem %zu B, %d CTAs/SM (%d with TMEM state, %d columns)\n", h->hdr.table,
                 h->hdr.split_steps ? "split" : "wavefront", h->ldpc_smem, h->ldpc_ctas, h->ldpc_ctas_tmem, h->hdr.tmem_cols);
@@ -193,7 +195,7 @@ int ldpc_out_bytes(const BlobHeader& h, int output_mode) { return (output_mode ?
 // grid size: persistent CTAs, as many as are resident at once; in group mode a multiple of the group
 int ldpc_grid(const dvbs2b200_code* h, int frames, int group, bool tmem)
 {
-    const int resident = h->sm_count * (tmem ? h->ldpc_ctas_tmem : h->ldpc_ctas);
+    const int resident = h->sm_count * ((tmem && !h->hdr.split_steps) ? h->ldpc_ctas_tmem : h->ldpc_ctas);
     int grid = std::min(frames, resident);
     if (group > 1)
         grid = std::min(frames, (resident / group) * group);
@@ -240,7 +242,9 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
     const int group = term_group > 1 ? term_group : 0;
     // wavefront state in tensor memory: per-frame mode only (the cooperative launch of the group mode is
     // sized by the occupancy calculator, which does not co-schedule kernels that use TMEM)
-    const bool tmem = group == 0 && h->ldpc_ctas_tmem >= h->ldpc_ctas && h->ldpc_ctas_tmem > 0 && !getenv("DVBS2B200_NO_TMEM");
+    // fourth kernel-variant flag: tensor-memory state (wavefront build) / out-of-line level calls (split build)
+    const bool tmem = hd.split_steps ? (hd.level_calls != 0 && hd.max_cnt <= 13)
+                                     : (group == 0 && h->ldpc_ctas_tmem >= h->ldpc_ctas && h->ldpc_ctas_tmem > 0 && !getenv("DVBS2B200_NO_TMEM"));
     const int grid = ldpc_grid(h, frames, group, tmem);
     {
         int rc = h->d_scratch.ensure((size_t)grid * hd.R * hd.msg_words * sizeof(uint32_t));

@@ -37,28 +37,42 @@ const ModcodDef* find_modcod(int standard, int framesize, int rate)
 // such layers we compute level[j] = 1 + max(level[j'] : j' < j touches one of j's bits); check
 // nodes of equal level are independent, and running the levels in order reproduces the serial
 // result bit for bit.
-// Which form of the conflict layers is faster was measured per code on B200 (profiles/r01b_sweep_*.jsonl).
-// Split steps win wherever the conflict layers carry one doubled group (the chain form: DVB-S2 1/2, 3/5, 3/4
-// normal, 2/3 short: +3 .. +40 %); layers with several doubled groups or a tripled one fall back to the
-// level-by-level form, and when those dominate on high-degree check nodes (9/10 normal: 13 of 18 layers) the
-// wavefront form with link-parallel runs stays ahead.
+// Which form of the conflict layers is faster was measured per code on B200 (profiles/r01b_sweep_configs.jsonl):
+// with the call-free split kernel the split steps win on all five BASELINE codes (1/2 normal 82 k -> 97 k,
+// 3/4 normal 77 k -> 133 k, 3/5 normal 70 k -> 91 k, 2/3 short 100 k -> 155 k, 9/10 normal 70 k -> 80 k frames/s),
+// so they are the default; the wavefront build stays in the library for A/B runs (DVBS2B200_SPLIT=0).
 bool choose_split(const LdpcTableDef& def)
 {
+    (void)def;
     if (const char* env = getenv("DVBS2B200_SPLIT"))
+        return atoi(env) != 0;
+    return true;
+}
+
+// Split build, which kernel variant: with or without the out-of-line level-form copies (ldpc_kernel.cu).
+// Measured on B200: the call-free variant wins wherever most conflict layers take the chain form (1/2 normal
+// 84 k -> 97 k, 3/4 normal 118 k -> 132 k frames/s: no local-memory frame, DRAM traffic back to the compulsory
+// bytes); short frames with a good share of three/four-link level-form layers keep the calls (2/3 short:
+// 119 k without, 154 k with).  DVBS2B200_LEVEL_CALLS=0/1 overrides.
+bool choose_level_calls(const LdpcTableDef& def)
+{
+    if (const char* env = getenv("DVBS2B200_LEVEL_CALLS"))
         return atoi(env) != 0;
     std::vector<std::vector<int>> groups(def.q);
     for (int c = 0; c < def.n_circ; ++c)
         groups[def.circ[c] >> 17].push_back((int)((def.circ[c] >> 9) & 0xff));
-    int multi = 0; // conflict layers that cannot take the chain form
+    int conflict = 0, level_form = 0, max_cnt = 0;
     for (auto& g : groups) {
         std::sort(g.begin(), g.end());
+        max_cnt = std::max(max_cnt, (int)g.size());
         int shared = 0;
         for (size_t a = 0; a < g.size(); ++a)
             if ((a && g[a] == g[a - 1]) || (a + 1 < g.size() && g[a] == g[a + 1]))
                 ++shared;
-        multi += shared > 2;
+        conflict += shared > 0;
+        level_form += shared > 2;
     }
-    return 3 * multi <= def.q;
+    return def.N <= 16200 && max_cnt <= 13 && 4 * level_form >= conflict && level_form > 0;
 }
 
 void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem, int split_arg)
@@ -433,6 +447,7 @@ bool build_blob(int standard, int framesize, int rate, std::vector<uint8_t>& blo
     h.bch_shorten = ((1u << h.gf_m) - 1) - (uint32_t)mc->nbch;
     h.split_steps = s.split ? 1u : 0u;
     h.chain_scratch = s.has_chain ? 1u : 0u;
+    h.level_calls = (s.split && choose_level_calls(def)) ? 1u : 0u;
 
     size_t off = sizeof(BlobHeader);
     h.smem_off = (uint32_t)off;

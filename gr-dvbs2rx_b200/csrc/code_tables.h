@@ -29,7 +29,7 @@ const ModcodDef* find_modcod(int standard, int framesize, int rate);
 
 // ---- packed blob ---------------------------------------------------------------------------
 constexpr uint32_t kBlobMagic = 0x32425344u; // "DSB2"
-constexpr uint32_t kBlobVersion = 12;
+constexpr uint32_t kBlobVersion = 13;
 
 // One per layer, 8 bytes, lives in shared memory.
 struct LayerRec {
@@ -114,7 +114,7 @@ struct BlobHeader {
     uint32_t bch_shorten;          // s = 2^m - 1 - nbch
     uint32_t split_steps;          // 1: conflict layers are split steps (kernels of the _split build), 0: wavefront steps
     uint32_t chain_scratch;        // 1: some split step is in chain form: the kernel needs the 360 x 8 B node scratch
-    uint32_t reserved1[1];
+    uint32_t level_calls;          // 1: split build, level-form steps through the out-of-line compile-time-count copies
 };
 static_assert(sizeof(BlobHeader) % 16 == 0, "header must keep sections 16-byte aligned");
 
@@ -154,6 +154,7 @@ struct Schedule {
 // split: 1 / 0 force the form of the conflict layers, -1 lets choose_split() decide (env DVBS2B200_SPLIT overrides)
 void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem = true, int split = -1);
 bool choose_split(const LdpcTableDef& def);
+bool choose_level_calls(const LdpcTableDef& def);
 
 // ---- GF(2^m) / BCH host helpers --------------------------------------------------------------
 uint32_t bch_prim_poly(int framesize); // lib/bch_decoder_bb_impl.cc:58-63

@@ -485,7 +485,7 @@ __device__ __forceinline__ void split_writeback(int hsel, int k0h, int k1h, int 
 // Not inlined: one copy per (NSH, WIDE) serves every kernel instantiation, and the register allocation of the
 // hot conflict-free pair step is not burdened with this code.
 template <int NSH, bool WIDE>
-__device__ __noinline__ void split_levels(const SplitCtx<WIDE>* cp, uint32_t* io)
+__device__ __forceinline__ void split_levels(const SplitCtx<WIDE>* cp, uint32_t* io)
 {
     const SplitCtx<WIDE> c = *cp;
     uint32_t k0 = io[0], k1 = io[1], sx = io[2], shs_lo = 0, shs_hi = 0;
@@ -559,6 +559,16 @@ __device__ __noinline__ void split_levels(const SplitCtx<WIDE>* cp, uint32_t* io
     }
     io[0] = k0, io[1] = k1, io[2] = sx, io[3] = shs_lo, io[4] = shs_hi;
 }
+// Out-of-line copies with compile-time link counts.  A call in the kernel costs every thread a local-memory
+// frame (register saves around it), whose traffic competes with the check-node state in L2: codes whose
+// conflict layers mostly take the chain form run the kernel variant WITHOUT these calls (one inlined rolled
+// loop for the few level-form layers, no stack at all); codes with many level-form layers of three or four
+// shared links (2/3 short) are faster with them.  The host chooses (code_tables.cc:choose_level_calls).
+template <int NSH, bool WIDE>
+__device__ __noinline__ void split_levels_call(const SplitCtx<WIDE>* cp, uint32_t* io)
+{
+    split_levels<NSH, WIDE>(cp, io);
+}
 
 // ---- chain form of phase 2 (code_tables.h) ------------------------------------------------------------
 // Node record in the shared-memory scratch, written by phase 1 and rewritten by the walk:
@@ -578,7 +588,7 @@ __device__ __forceinline__ int chain_operand_addr(const uint2 e, int j)
 // bit the next node reads through its "in" link: it travels in a register.  A chain's last node meets, through
 // its out link, the bit that the first node of some chain updated through its in link at step 0 -- hence one
 // barrier among the walking warps after step 0, and none after that.
-__device__ __noinline__ void split_chain_walk(int8_t* __restrict__ L, uint2* __restrict__ rec, const uint2 e_in, const uint2 e_out,
+__device__ __forceinline__ void split_chain_walk(int8_t* __restrict__ L, uint2* __restrict__ rec, const uint2 e_in, const uint2 e_out,
                                               int d_in, int d_out, int in_is_link1, int delta, int tid)
 {
     // called by every lane of the first ceil(delta / 32) warps (the barrier below is warp granular)
@@ -652,8 +662,8 @@ __device__ __noinline__ void split_chain_walk(int8_t* __restrict__ L, uint2* __r
     }
 }
 
-template <int CNT_MAX, bool UNIFORM, bool WIDE, bool SELF_CHECK>
-__device__ __noinline__ int process_split(int8_t* __restrict__ L, const uint2* __restrict__ edges, const LayerView lv, int layer,
+template <int CNT_MAX, bool UNIFORM, bool WIDE, bool SELF_CHECK, bool LEVEL_CALLS>
+__device__ __forceinline__ int process_split(int8_t* __restrict__ L, const uint2* __restrict__ edges, const LayerView lv, int layer,
                                              int p, bool active, int K, int q, uint32_t wA, uint32_t wB, uint32_t sA, uint32_t sB,
                                              uint32_t* __restrict__ msg_out, uint64_t pol, int depth, const uint16_t* __restrict__ level_tab,
                                              volatile int* progress, unsigned long long* prof, uint2* __restrict__ rec, bool chain, int chain_delta, int chain_out_link)
@@ -681,27 +691,26 @@ __device__ __noinline__ int process_split(int8_t* __restrict__ L, const uint2* _
         nsg_lo = ~((sA & 0xffffu) | (sB << 16));
         nsg_hi = ~((sA >> 16) | (sB & 0xffff0000u));
     }
-    int adr[DEG_MAX];
-    uint32_t sel[DEG_MAX];
-    uint32_t v[DEG_MAX], mag[DEG_MAX];
+    // Only the private links' x values stay live across phase 2; addresses, selectors and magnitudes are
+    // recomputed in phase 3 (a few instructions per link), which keeps the step inside the register budget
+    // with phase 2 inlined.
+    uint32_t v[DEG_MAX];
     const int c = q * p + layer;
-    adr[0] = K + 2 * c;
-    sel[0] = 0x9180u | (0x4420u << 16);
-    adr[1] = first ? K + 2 * (half - 1) : K + 2 * c - 2;
-    sel[1] = first ? (0x8091u | (0x4402u << 16)) : sel[0];
     const uint32_t pkey = ((uint32_t)p << 16) | 0xffffu;
-#pragma unroll
-    for (int d = 0; d < CNT_MAX; ++d) {
-        if (UNIFORM || d < lv.cnt) {
-            const uint2 e = edges[lv.edge_begin + d];
-            const bool lt = e.x > pkey;
-            adr[d + 2] = (int)(e.x & 0xffffu) + 2 * p - (lt ? 0 : 360);
-            sel[d + 2] = lt ? (e.y ^ 0x00221111u) : e.y;
+    auto link_addr = [&](int d, int& adr, uint32_t& sel) {
+        if (d == 0) {
+            adr = K + 2 * c;
+            sel = 0x9180u | (0x4420u << 16);
+        } else if (d == 1) {
+            adr = first ? K + 2 * (half - 1) : K + 2 * c - 2;
+            sel = first ? (0x8091u | (0x4402u << 16)) : (0x9180u | (0x4420u << 16));
         } else {
-            adr[d + 2] = 0;
-            sel[d + 2] = 0;
+            const uint2 e = edges[lv.edge_begin + d - 2];
+            const bool lt = e.x > pkey;
+            adr = (int)(e.x & 0xffffu) + 2 * p - (lt ? 0 : 360);
+            sel = lt ? (e.y ^ 0x00221111u) : e.y;
         }
-    }
+    };
     const uint32_t n0p = vsub(0u, vmin(m0, h2(31))), n1p = vsub(0u, vmin(m1, h2(31)));
     const uint32_t nx01p = n0p ^ n1p;
     uint32_t k0 = h2(0x7fff), k1 = h2(0x7fff), sx = 0;
@@ -710,8 +719,11 @@ __device__ __noinline__ int process_split(int8_t* __restrict__ L, const uint2* _
         for (int d = 0; d < DEG_MAX; ++d) {
             const bool live = (d < 2) || (d - 2 < npriv);
             if (live) {
-                const uint32_t raw = *reinterpret_cast<const uint16_t*>(L + adr[d]);
-                const uint32_t l = prmt(raw, 0, sel[d]);
+                int adr;
+                uint32_t sel;
+                link_addr(d, adr, sel);
+                const uint32_t raw = *reinterpret_cast<const uint16_t*>(L + adr);
+                const uint32_t l = prmt(raw, 0, sel);
                 const uint32_t hot = (!WIDE || d < 16) ? hot_lo : hot_hi;
                 const uint32_t nsg = (!WIDE || d < 16) ? nsg_lo : nsg_hi;
                 const uint32_t im = signmask(hot << (15 - (d & 15)));
@@ -724,7 +736,6 @@ __device__ __noinline__ int process_split(int8_t* __restrict__ L, const uint2* _
                 v[d] = x;
                 sx ^= x;
                 const uint32_t mg = vmin(vmax(vmax(vadd(x, h2(-1)), ~x), 0u), h2(126));
-                mag[d] = mg;
                 uint32_t key = imad(mg, 32u, h2(d));
                 if (d == 1 && first)
                     key |= 0x00007fffu;
@@ -732,7 +743,6 @@ __device__ __noinline__ int process_split(int8_t* __restrict__ L, const uint2* _
                 k0 = vmin(k0, key);
             } else {
                 v[d] = 0;
-                mag[d] = 0;
             }
         }
     }
@@ -812,11 +822,15 @@ __device__ __noinline__ int process_split(int8_t* __restrict__ L, const uint2* _
         SplitCtx<WIDE> cx = { L, edges + lv.edge_begin + npriv, level_tab, progress, p, pkey, 2 + npriv, lv.nshared, depth, lvA, lvB,
                               active, wA, wB, sA, sB, prof };
         uint32_t io[5] = { k0, k1, sx, 0u, 0u };
-        switch (lv.nshared) { // compile-time link counts for the common cases, a rolled loop for the rest
-        case 2: split_levels<2, WIDE>(&cx, io); break;
-        case 3: split_levels<3, WIDE>(&cx, io); break;
-        case 4: split_levels<4, WIDE>(&cx, io); break;
-        default: split_levels<0, WIDE>(&cx, io); break;
+        if (!LEVEL_CALLS) {
+            split_levels<0, WIDE>(&cx, io); // one rolled variant, inlined: no call in this kernel variant
+        } else {
+            switch (lv.nshared) { // compile-time link counts for the common cases, a rolled loop for the rest
+            case 2: split_levels_call<2, WIDE>(&cx, io); break;
+            case 3: split_levels_call<3, WIDE>(&cx, io); break;
+            case 4: split_levels_call<4, WIDE>(&cx, io); break;
+            default: split_levels_call<0, WIDE>(&cx, io); break;
+            }
         }
         k0 = io[0], k1 = io[1], sx = io[2], shs_lo = io[3], shs_hi = io[4];
     }
@@ -839,16 +853,20 @@ __device__ __noinline__ int process_split(int8_t* __restrict__ L, const uint2* _
         else
             newsg_hi = vadd(newsg_hi, newsg_hi);
         if (live) {
-            const uint32_t t = vmin(mag[d], min1);
+            int adr;
+            uint32_t sel;
+            link_addr(d, adr, sel);
+            const uint32_t mg = vmin(vmax(vmax(vadd(v[d], h2(-1)), ~v[d]), 0u), h2(126));
+            const uint32_t t = vmin(mg, min1);
             const uint32_t np = vadd(vadd(v[d], s01p1), ~t);
             const uint32_t nn = vadd(vadd(v[d], ns01), t);
             const uint32_t ng = signmask(sx ^ v[d]);
             const uint32_t nl = vmin(vmax(bsel(ng, nn, np), h2(-128)), h2(127));
-            const uint32_t packed = prmt(nl, 0, sel[d] >> 16);
+            const uint32_t packed = prmt(nl, 0, sel >> 16);
             if (d == 1 && first)
-                L[adr[d]] = (int8_t)(nl >> 16);
+                L[adr] = (int8_t)(nl >> 16);
             else
-                *reinterpret_cast<uint16_t*>(L + adr[d]) = (uint16_t)packed;
+                *reinterpret_cast<uint16_t*>(L + adr) = (uint16_t)packed;
             const uint32_t bit = ng & 0x00010001u;
             if (!WIDE || d < 16)
                 newsg_lo = vadd(newsg_lo, bit);
@@ -862,8 +880,11 @@ __device__ __noinline__ int process_split(int8_t* __restrict__ L, const uint2* _
                 zer |= vsub(nlc, h2(1)) & ~nlc;
             }
         } else if (SELF_CHECK && (UNIFORM || d - 2 < lv.cnt)) {
-            const uint32_t raw = *reinterpret_cast<const uint16_t*>(L + adr[d]);
-            const uint32_t nlc = prmt(raw, 0, sel[d]);
+            int adr;
+            uint32_t sel;
+            link_addr(d, adr, sel);
+            const uint32_t raw = *reinterpret_cast<const uint16_t*>(L + adr);
+            const uint32_t nlc = prmt(raw, 0, sel);
             syn ^= nlc;
             zer |= vsub(nlc, h2(1)) & ~nlc;
         }
@@ -1246,6 +1267,8 @@ __device__ __forceinline__ uint32_t check_pair(const int8_t* __restrict__ L, con
 template <int CNT_MAX, bool UNIFORM, bool WIDE, bool TMEM>
 __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kernel(const LdpcLaunch p)
 {
+    // fourth template flag: tensor-memory state (wavefront build) / out-of-line level calls (split build)
+    constexpr bool USE_TMEM = TMEM && DVBS2_LEGACY_WAVEFRONT;
     extern __shared__ __align__(16) uint8_t smem[];
     int8_t* const L = reinterpret_cast<int8_t*>(smem);
     const uint2* layers = reinterpret_cast<const uint2*>(smem + p.smem_tab_off);
@@ -1272,18 +1295,18 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // tensor memory for the state of the order-sensitive layers: warp 0 allocates (and frees at the end)
-    if (TMEM && tid < 32) {
+    if (USE_TMEM && tid < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "n"(kTmemColsDev)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (TMEM)
+    if (USE_TMEM)
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (TMEM)
+    if (USE_TMEM)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = TMEM ? s_tmem_base : 0u;
-    const uint32_t tmem_warp = tmem_base + ((uint32_t)((tid >> 5) & 3) << 21); // this warp's 32 TMEM lanes
+    const uint32_t tmem_base = USE_TMEM ? s_tmem_base : 0u;
+    const uint32_t tmem_warp = tmem_base + ((uint32_t)((tid >> 5) & 3) << 21); // this warp's 32 USE_TMEM lanes
     (void)tmem_warp;
     (void)tcol;
     // stage the code tables once per CTA (TMA)
@@ -1449,10 +1472,10 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
                     // conflict layer, pair mapping kept: private links in s16x2, shared links level by level
                     uint32_t* mo = msg + ((size_t)layer * kPairs + (tid < kPairs ? tid : 0)) * 2 * MW;
                     if (last)
-                        self_bad |= process_split<CNT_MAX, UNIFORM, WIDE, true>(L, edges, lv, layer, tid, tid < kPairs, K, q, cA, cB, csA, csB, mo,
+                        self_bad |= process_split<CNT_MAX, UNIFORM, WIDE, true, TMEM>(L, edges, lv, layer, tid, tid < kPairs, K, q, cA, cB, csA, csB, mo,
                                                                                 pol_keep, count, work + work_off, &s_progress, p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr, rec, is_chain, run_len, (int)link_parallel);
                     else
-                        process_split<CNT_MAX, UNIFORM, WIDE, false>(L, edges, lv, layer, tid, tid < kPairs, K, q, cA, cB, csA, csB, mo, pol_keep,
+                        process_split<CNT_MAX, UNIFORM, WIDE, false, TMEM>(L, edges, lv, layer, tid, tid < kPairs, K, q, cA, cB, csA, csB, mo, pol_keep,
                                                                      count, work + work_off, &s_progress, p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr, rec, is_chain, run_len, (int)link_parallel);
                 }
 #else
@@ -1469,11 +1492,11 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
                 } else {
                     // wide wavefront level: single check nodes, one per thread
                     const uint32_t tc = tcol[s];
-                    if (TMEM && tc != 0xffu) {
+                    if (USE_TMEM && tc != 0xffu) {
                         // state in tensor memory: a column per 4 warps and pass, lane = thread
                         for (int t0 = 0; t0 < count; t0 += kLdpcThreads) {
                             const int t = t0 + tid;
-                            if (t0 + (tid & ~31) < count) { // warp-uniform: TMEM accesses are warp collectives
+                            if (t0 + (tid & ~31) < count) { // warp-uniform: USE_TMEM accesses are warp collectives
                                 const uint32_t taddr = tmem_warp + tc + 2u * (uint32_t)(t0 / kLdpcThreads) + (uint32_t)(tid >> 7);
                                 uint32_t w = zero_state ? 0u : tmem_ld(taddr);
                                 if (t < count) {
@@ -1552,7 +1575,7 @@ __global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kern
         __syncthreads(); // L is reused by the next frame
         LAP(6);
     }
-    if (TMEM) {
+    if (USE_TMEM) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         if (tid < 32)
@@ -1588,7 +1611,7 @@ int occupancy_one(size_t smem)
     auto kern = ldpc_decode_kernel<CNT_MAX, UNIFORM, WIDE, TMEM>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return 0;
-    if (!TMEM) {
+    if (!(TMEM && DVBS2_LEGACY_WAVEFRONT)) {
         int n = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kLdpcThreads, smem) != cudaSuccess)
             return 0;
@@ -1653,11 +1676,9 @@ bool ldpc_wide_state(int max_cnt) { return max_cnt > 13; }
 // (every DVB-S2 normal-frame table) get the link count as a compile-time constant: no predication,
 // no dead link slots.  The rest take the predicated variant of the next size up.  The narrow state
 // word holds 15 sign bits (<= 13 data links), above that the wide (two-word) state is used.
-#if DVBS2_LEGACY_WAVEFRONT
+// The fourth template flag is "wavefront state in tensor memory" in the wavefront build and "level-form split
+// steps through out-of-line calls" in the split build (narrow-state codes only in both).
 #define DVBS2_TM(CALL, C, U) (tmem ? CALL(C, U, false, true) : CALL(C, U, false, false))
-#else
-#define DVBS2_TM(CALL, C, U) CALL(C, U, false, false)
-#endif
 #define DVBS2_DISPATCH(CALL)                                   \
     if (uniform) {                                             \
         switch (max_cnt) {                                     \
@@ -1693,8 +1714,6 @@ cudaError_t LDPC_SYM(ldpc_launch)(const LdpcLaunch& p, int max_cnt, bool uniform
 
 int LDPC_SYM(ldpc_ctas_per_sm)(int max_cnt, bool uniform, bool tmem, size_t smem)
 {
-    if (tmem && !DVBS2_LEGACY_WAVEFRONT)
-        return 0; // the tensor-memory variant belongs to the legacy wavefront paths
 #define CALL(C, U, W, T) occupancy_one<C, U, W, T>(smem)
     DVBS2_DISPATCH(CALL)
 #undef CALL
