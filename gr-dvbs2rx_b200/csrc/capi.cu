@@ -151,6 +151,10 @@ int create_from_blob(dvbs2b200_code** out, int device, std::vector<uint8_t>&& bl
         return bail(cuda_fail(e, "cudaMalloc(tables)"));
     if ((e = cudaMemcpy(h->d_blob, h->blob.data(), h->blob.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
         return bail(cuda_fail(e, "cudaMemcpy(tables)"));
+    // a pageable-source copy may return while its DMA is still in flight on the legacy stream; the kernels
+    // run on non-blocking streams that do not order against it
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess)
+        return bail(cuda_fail(e, "cudaDeviceSynchronize(tables)"));
     h->ldpc_smem = ldpc_smem_bytes(h->hdr.N, h->hdr.smem_bytes, h->hdr.chain_scratch != 0, nullptr);
     auto ctas_per_sm = h->hdr.split_steps ? ldpc_ctas_per_sm_split : ldpc_ctas_per_sm_wavefront;
     if (h->hdr.max_cnt <= 28 && h->ldpc_smem <= (size_t)h->smem_optin)
@@ -455,8 +459,11 @@ int bb_ensure(dvbs2b200_code* h)
         return rc;
     std::vector<uint8_t> seq;
     bb_prbs(seq, hd.kbch / 8);
-    CU(cudaMemcpy(h->d_prbs.p, seq.data(), seq.size(), cudaMemcpyHostToDevice));
-    CU(cudaMemset(h->d_bbstate.p, 0, sizeof(BbState)));
+    // on the handle's stream: a plain cudaMemset runs on the legacy default stream, asynchronously with
+    // respect to the host, and would race with the first kernels on the (non-blocking) handle stream
+    CU(cudaMemcpyAsync(h->d_prbs.p, seq.data(), seq.size(), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(h->d_bbstate.p, 0, sizeof(BbState), h->stream));
+    CU(cudaStreamSynchronize(h->stream)); // seq is a local
     h->bb_ready = true;
     return DVBS2B200_OK;
 }
@@ -1352,8 +1359,8 @@ int dvbs2b200_bb_reset(dvbs2b200_code* h)
     int rc = bb_ensure(h);
     if (rc)
         return rc;
+    CU(cudaMemsetAsync(h->d_bbstate.p, 0, sizeof(BbState), h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    CU(cudaMemset(h->d_bbstate.p, 0, sizeof(BbState)));
     return DVBS2B200_OK;
 }
 

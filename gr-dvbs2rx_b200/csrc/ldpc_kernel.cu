@@ -42,6 +42,11 @@
 #ifndef DVBS2_LEGACY_WAVEFRONT
 #define DVBS2_LEGACY_WAVEFRONT 0
 #endif
+// Split build: kernels for codes with at least this many data links per check node are compiled for two
+// resident CTAs per SM (168 registers, no spills) instead of three (96 registers, spilling)
+#ifndef DVBS2_TWO_CTA_FROM
+#define DVBS2_TWO_CTA_FROM 11
+#endif
 #if DVBS2_LEGACY_WAVEFRONT
 #define LDPC_SYM(x) x##_wavefront
 #else
@@ -1265,7 +1270,8 @@ __device__ __forceinline__ uint32_t check_pair(const int8_t* __restrict__ L, con
 }
 
 template <int CNT_MAX, bool UNIFORM, bool WIDE, bool TMEM>
-__global__ void __launch_bounds__(kLdpcThreads, kLdpcCtasPerSm) ldpc_decode_kernel(const LdpcLaunch p)
+__global__ void __launch_bounds__(kLdpcThreads, (DVBS2_LEGACY_WAVEFRONT || CNT_MAX < DVBS2_TWO_CTA_FROM) ? kLdpcCtasPerSm : 2)
+    ldpc_decode_kernel(const LdpcLaunch p)
 {
     // fourth template flag: tensor-memory state (wavefront build) / out-of-line level calls (split build)
     constexpr bool USE_TMEM = TMEM && DVBS2_LEGACY_WAVEFRONT;
