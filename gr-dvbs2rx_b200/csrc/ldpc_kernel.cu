@@ -271,8 +271,8 @@ __device__ __forceinline__ int process_pair(int8_t* __restrict__ L, const uint2*
             // stored message: +-(d == argmin ? min1 : min0), clamped to [-32, 31]
             const uint32_t hot = (!WIDE || d < 16) ? hot_lo : hot_hi;
             const uint32_t nsg = (!WIDE || d < 16) ? nsg_lo : nsg_hi;
-            const uint32_t im = signmask(hot << (15 - (d & 15)));
-            const uint32_t nm = signmask(nsg << (15 - (d & 15))); // 0xFFFF where the old message was >= 0
+            const uint32_t im = signmask(imad(hot, 1u << (15 - (d & 15)), 0u)); // the shift as IMAD: FMA pipe, not ALU
+            const uint32_t nm = signmask(imad(nsg, 1u << (15 - (d & 15)), 0u)); // 0xFFFF where the old message was >= 0
             const uint32_t xa = vadd(l, n0p ^ (nx01p & im));      // l - old, old >= 0
             const uint32_t xb = vadd(l, m0 ^ (x01 & im));         // l - old, old < 0
             uint32_t x = vmin(vmax(bsel(nm, xa, xb), h2(-128)), h2(127)); // vqsub
@@ -281,7 +281,7 @@ __device__ __forceinline__ int process_pair(int8_t* __restrict__ L, const uint2*
             v[d] = x;
             sx ^= x;
             // |x| saturated to 127, minus beta = 1, floored at 0:  max(x - 1, ~x, 0), capped at 126
-            const uint32_t mg = vmin(vmax(vmax(vadd(x, h2(-1)), ~x), 0u), h2(126));
+            const uint32_t mg = vmax(vmax(vadd(x, h2(-1)), ~x), 0u); // (the cap at 126 for x = -128 is applied to the two minima)
             mag[d] = mg;
             uint32_t key = imad(mg, 32u, h2(d));
             if (d == 1 && first)
@@ -293,8 +293,9 @@ __device__ __forceinline__ int process_pair(int8_t* __restrict__ L, const uint2*
             mag[d] = 0;
         }
     }
-    const uint32_t min0 = (k0 >> 5) & 0x07ff07ffu;
-    const uint32_t min1 = (k1 >> 5) & 0x07ff07ffu;
+    // order statistics commute with the monotone cap: min(|x|, 127) - 1 <= 126 taken once per minimum, not per link
+    const uint32_t min0 = vmin((k0 >> 5) & 0x07ff07ffu, h2(126));
+    const uint32_t min1 = vmin((k1 >> 5) & 0x07ff07ffu, h2(126));
     // new posterior = v +- m, m = min over the OTHER links = min0 + min1 - min(mag, min1):
     //   v + m = (v + s01 + 1) + ~t,   v - m = (v - s01) + t,   t = min(mag, min1)
     const uint32_t s01 = vadd(min0, min1);
@@ -319,11 +320,11 @@ __device__ __forceinline__ int process_pair(int8_t* __restrict__ L, const uint2*
                 L[adr[d]] = (int8_t)(nl >> 16); // only node B's link exists (low byte of that word)
             else
                 *reinterpret_cast<uint16_t*>(L + adr[d]) = (uint16_t)packed;
-            const uint32_t bit = ng & 0x00010001u;
+            // ng is 0xFFFF = -1 in a half whose new message is negative: subtracting it shifts a 1 in
             if (!WIDE || d < 16)
-                newsg_lo = vadd(newsg_lo, bit);
+                newsg_lo = vsub(newsg_lo, ng);
             else
-                newsg_hi = vadd(newsg_hi, bit);
+                newsg_hi = vsub(newsg_hi, ng);
             if (SELF_CHECK) {
                 uint32_t nlc = nl;
                 if (d == 1 && first)
@@ -731,8 +732,8 @@ __device__ __forceinline__ int process_split(int8_t* __restrict__ L, const uint2
                 const uint32_t l = prmt(raw, 0, sel);
                 const uint32_t hot = (!WIDE || d < 16) ? hot_lo : hot_hi;
                 const uint32_t nsg = (!WIDE || d < 16) ? nsg_lo : nsg_hi;
-                const uint32_t im = signmask(hot << (15 - (d & 15)));
-                const uint32_t nm = signmask(nsg << (15 - (d & 15)));
+                const uint32_t im = signmask(imad(hot, 1u << (15 - (d & 15)), 0u)); // the shift as IMAD: FMA pipe, not ALU
+                const uint32_t nm = signmask(imad(nsg, 1u << (15 - (d & 15)), 0u));
                 const uint32_t xa = vadd(l, n0p ^ (nx01p & im));
                 const uint32_t xb = vadd(l, m0 ^ (x01 & im));
                 uint32_t x = vmin(vmax(bsel(nm, xa, xb), h2(-128)), h2(127));
@@ -872,11 +873,11 @@ __device__ __forceinline__ int process_split(int8_t* __restrict__ L, const uint2
                 L[adr] = (int8_t)(nl >> 16);
             else
                 *reinterpret_cast<uint16_t*>(L + adr) = (uint16_t)packed;
-            const uint32_t bit = ng & 0x00010001u;
+            // ng is 0xFFFF = -1 in a half whose new message is negative: subtracting it shifts a 1 in
             if (!WIDE || d < 16)
-                newsg_lo = vadd(newsg_lo, bit);
+                newsg_lo = vsub(newsg_lo, ng);
             else
-                newsg_hi = vadd(newsg_hi, bit);
+                newsg_hi = vsub(newsg_hi, ng);
             if (SELF_CHECK) {
                 uint32_t nlc = nl;
                 if (d == 1 && first)

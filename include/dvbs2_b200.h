@@ -216,7 +216,8 @@ size_t dvbs2b200_bb_ts_capacity(const dvbs2b200_code* h, int frames);
 int dvbs2b200_bb_deheader(dvbs2b200_code* h, const uint8_t* bbframes, int frames, int scrambled, uint8_t* ts,
                           size_t ts_cap, size_t* ts_bytes);
 /* device variant: the byte count of the call is read back with dvbs2b200_bb_produced_dev after the stream
- * has been synchronised (it lives in the handle's device state). */
+ * has been synchronised (it lives in the handle's device state).  d_ts must be 4-byte aligned (packets are
+ * written as 32-bit words); d_bbframes may have any alignment. */
 int dvbs2b200_bb_deheader_dev(dvbs2b200_code* h, const uint8_t* d_bbframes, int frames, int scrambled,
                               uint8_t* d_ts, size_t ts_cap, void* stream);
 int dvbs2b200_bb_produced_dev(dvbs2b200_code* h, void* stream, size_t* ts_bytes);

@@ -5,6 +5,7 @@
     python tools/run_one.py ts    C1_2 1 2.0 25 2664     # LDPC + BCH + descrambler + deheader -> TS packets
     python tools/run_one.py bb    C1_2 1 0 0 8192        # descrambler + deheader alone on clean BBFRAMEs
     python tools/run_one.py snr   C3_5 1 6.2 0 2664      # SNR estimate (8PSK for 3/5, else QPSK) + demap
+    python tools/run_one.py mixed C1_2 1 0 25 5000       # five MODCODs interleaved in one batch (host API)
 
 Prints device time per pass (CUDA events) and the derived rates; not the bench line."""
 import os
@@ -72,6 +73,34 @@ if what in ("fec", "ts"):
         t = timed(run)
         print("ts %s: %.3f ms, %.0f frames/s, %d TS bytes, counters %s" % (rate_name, t * 1e3, F / t, code.bb_produced_dev(stream),
                                                                         code.bb_counters()))
+elif what == "mixed":
+    # BASELINE config 5: the five MODCODs interleaved in one batch, per-frame code id, host buffers in and out
+    import time
+    modcods = [(0, 1, d.C1_2, 2.0), (0, 1, d.C3_4, 4.6), (0, 1, d.C3_5, 3.5), (0, 0, d.C2_3, 4.2), (0, 1, d.C9_10, 6.6)]
+    mixed = d.MixedCodes([m[:3] for m in modcods])
+    per = F // len(modcods)
+    llrs, ids = [], []
+    for c, (std, f_s, r, e) in enumerate(modcods):
+        msg, cw, llr, inf = vectors.make_llr_frames(std, f_s, r, 32, e, seed=70 + c)
+        llrs.append(np.tile(llr, (per // 32 + 1, 1))[:per])
+        ids.append(np.full(per, c, dtype=np.uint8))
+    order = np.concatenate(ids)
+    perm = rng.permutation(order.size)
+    order = order[perm]
+    counters = [0] * len(modcods)
+    parts = []
+    for c in order:
+        parts.append(llrs[c][counters[c]])
+        counters[c] += 1
+    cat = np.concatenate(parts)
+    mixed.fec_decode(order, cat, trials)
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        msg, tr, co = mixed.fec_decode(order, cat, trials)
+    t = (time.perf_counter() - t0) / reps
+    print("mixed: %d frames of %d MODCODs, %.1f ms per batch through the host API, %.0f frames/s, %.0f%% converged" % (
+        order.size, len(modcods), t * 1e3, order.size / t, 100.0 * (tr >= 0).mean()))
 elif what == "bb":
     up, bb = bb_stream(F)
     d_bb = torch.from_numpy(bbf.scramble(bb)).to(dev)
