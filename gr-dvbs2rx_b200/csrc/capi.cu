@@ -85,6 +85,7 @@ struct dvbs2b200_code {
     DevBuf d_in, d_mid, d_out, d_post, d_i32a, d_i32b, d_n0, d_llr, d_sync, d_scratch, d_flag, d_prof;
     // BB layer: descrambling sequence, deheader stream state, per-call scratch, TS output staging
     DevBuf d_prbs, d_bbstate, d_bbrec, d_bbplan, d_ts;
+    DevBuf d_points; // table-driven demapper: constellation [32][2] floats + row offsets [5] ints
     bool bb_ready = false;
 };
 
@@ -689,7 +690,7 @@ void dvbs2b200_code_destroy(dvbs2b200_code* h)
     if (h->stream)
         cudaStreamSynchronize(h->stream);
     for (DevBuf* b : { &h->d_in, &h->d_mid, &h->d_out, &h->d_post, &h->d_i32a, &h->d_i32b, &h->d_n0, &h->d_llr, &h->d_sync, &h->d_scratch, &h->d_flag, &h->d_prof,
-                       &h->d_prbs, &h->d_bbstate, &h->d_bbrec, &h->d_bbplan, &h->d_ts })
+                       &h->d_prbs, &h->d_bbstate, &h->d_bbrec, &h->d_bbplan, &h->d_ts, &h->d_points })
         b->release();
     if (h->d_blob)
         cudaFree(h->d_blob);
@@ -1217,6 +1218,92 @@ uint64_t dvbs2b200_mixed_launch_count(const dvbs2b200_mixed* m)
         for (const dvbs2b200_code* h : m->codes)
             n += h->launches;
     return n;
+}
+
+// ---- table-driven demapper (16APSK / 32APSK / any constellation of up to 32 points) ------------------
+int dvbs2b200_demap_table_dev(dvbs2b200_code* h, int bits, const float* points, const int* row_offsets, const float* d_iq,
+                              int frames, const float* d_n0, int8_t* d_llr, void* stream)
+{
+    if (!h)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    if (bits < 1 || bits > 5 || !points || !row_offsets)
+        return fail(DVBS2B200_EINVAL, "bits must be 1..5 with a constellation and row offsets");
+    const BlobHeader& hd = h->hdr;
+    if (hd.N % bits)
+        return fail(DVBS2B200_EINVAL, "frame length is not a multiple of the bits per symbol");
+    if (frames < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames");
+    if (frames == 0)
+        return DVBS2B200_OK;
+    if (!d_iq || !d_n0 || !d_llr)
+        return fail(DVBS2B200_EINVAL, "null buffer");
+    const int n_syms = hd.N / bits;
+    for (int k = 0; k < bits; ++k)
+        if (row_offsets[k] < 0 || row_offsets[k] + n_syms > hd.N)
+            return fail(DVBS2B200_EINVAL, "row offset out of range");
+    DeviceGuard g(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = h->d_points.ensure(32 * 2 * sizeof(float) + 8 * sizeof(int));
+    if (rc)
+        return rc;
+    // the table rides along with the call (320 bytes); staged copies are ordered on the caller's stream
+    float hp[64] = { 0 };
+    int hr[8] = { 0 };
+    memcpy(hp, points, sizeof(float) * 2 * ((size_t)1 << bits));
+    memcpy(hr, row_offsets, sizeof(int) * bits);
+    CU(cudaMemcpyAsync(h->d_points.p, hp, sizeof(hp), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync((uint8_t*)h->d_points.p + sizeof(hp), hr, sizeof(hr), cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s)); // hp / hr are locals
+    TableDemapLaunch p;
+    memset(&p, 0, sizeof(p));
+    p.points = (const float*)h->d_points.p;
+    p.row_off = (const int*)((uint8_t*)h->d_points.p + sizeof(hp));
+    p.n_syms = n_syms;
+    p.bits = bits;
+    for (int f0 = 0; f0 < frames; f0 += 32768) {
+        p.frames = std::min(32768, frames - f0);
+        p.iq = d_iq + (size_t)f0 * n_syms * 2;
+        p.n0 = d_n0 + f0;
+        p.llr = d_llr + (size_t)f0 * hd.N;
+        cudaError_t e = demap_table_launch(p, s);
+        if (e != cudaSuccess)
+            return cuda_fail(e, "demap_table_launch");
+        h->launches += 1;
+    }
+    return DVBS2B200_OK;
+}
+
+int dvbs2b200_demap_table(dvbs2b200_code* h, int bits, const float* points, const int* row_offsets, const float* iq, int frames,
+                          const float* n0, int8_t* llr)
+{
+    if (!h)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    if (bits < 1 || bits > 5)
+        return fail(DVBS2B200_EINVAL, "bits must be 1..5");
+    if (frames < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames");
+    if (frames == 0)
+        return DVBS2B200_OK;
+    if (!iq || !n0 || !llr)
+        return fail(DVBS2B200_EINVAL, "null buffer");
+    DeviceGuard g(h->device);
+    const BlobHeader& hd = h->hdr;
+    if (hd.N % bits)
+        return fail(DVBS2B200_EINVAL, "frame length is not a multiple of the bits per symbol");
+    const size_t iq_bytes = (size_t)frames * (hd.N / bits) * 8, llr_bytes = (size_t)frames * hd.N;
+    int rc;
+    if ((rc = h->d_in.ensure(iq_bytes)) || (rc = h->d_llr.ensure(llr_bytes)) || (rc = h->d_n0.ensure((size_t)frames * 4)))
+        return rc;
+    cudaStream_t s = h->stream;
+    CU(cudaMemcpyAsync(h->d_in.p, iq, iq_bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->d_n0.p, n0, (size_t)frames * 4, cudaMemcpyHostToDevice, s));
+    rc = dvbs2b200_demap_table_dev(h, bits, points, row_offsets, (const float*)h->d_in.p, frames, (const float*)h->d_n0.p,
+                                   (int8_t*)h->d_llr.p, s);
+    if (rc)
+        return rc;
+    CU(cudaMemcpyAsync(llr, h->d_llr.p, llr_bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return DVBS2B200_OK;
 }
 
 // ---- SNR estimate ---------------------------------------------------------------------------------

@@ -149,7 +149,64 @@ __global__ void __launch_bounds__(256) snr_kernel(const SnrLaunch p)
     }
 }
 
+// ---- table-driven max-log soft demapper (16APSK, 32APSK, any constellation of up to 32 points) -------------
+// The reference has no demapper beyond QPSK / 8PSK (lib/xfecframe_demapper_cb_impl.cc:70-72 throws), so there
+// is no parity target; this is SURVEY 8f rank 3, defined here as the max-log LLR
+//     llr_k = ( min_{s: bit k of s = 1} |y - s|^2  -  min_{s: bit k of s = 0} |y - s|^2 ) / N0
+// (positive = bit 0, the convention of lib/qpsk.h:208-214; for QPSK it reduces to the reference's 2 sqrt(2) x / N0),
+// rounded to nearest even and saturated to int8 like the other two.  Symbol index s = the symbol's bits, first
+// bit = MSB.  Bit k of symbol j goes to llr[row_off[k] + j]: the DVB-S2 block interleaver read back, any column
+// order.  One thread per symbol, the constellation in shared memory; stores coalesce per bit row.
+__global__ void __launch_bounds__(256) demap_table_kernel(const TableDemapLaunch p)
+{
+    __shared__ float2 s_pts[32];
+    __shared__ int s_row[5];
+    const int frame = blockIdx.y, npts = 1 << p.bits;
+    if (threadIdx.x < npts)
+        s_pts[threadIdx.x] = reinterpret_cast<const float2*>(p.points)[threadIdx.x];
+    if (threadIdx.x < p.bits)
+        s_row[threadIdx.x] = p.row_off[threadIdx.x];
+    __syncthreads();
+    const float inv_n0 = 1.0f / p.n0[frame];
+    const float2* __restrict__ in = reinterpret_cast<const float2*>(p.iq + (size_t)frame * p.n_syms * 2);
+    int8_t* __restrict__ out = p.llr + (size_t)frame * p.n_syms * p.bits;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p.n_syms; j += gridDim.x * blockDim.x) {
+        const float2 y = __ldcs(in + j);
+        float d0[5], d1[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            d0[k] = d1[k] = 3.0e38f;
+        for (int s = 0; s < npts; ++s) {
+            const float er = __fsub_rn(y.x, s_pts[s].x), ei = __fsub_rn(y.y, s_pts[s].y);
+            const float d = __fadd_rn(__fmul_rn(er, er), __fmul_rn(ei, ei));
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                if (k < p.bits) {
+                    const bool one = (s >> (p.bits - 1 - k)) & 1;
+                    if (one)
+                        d1[k] = fminf(d1[k], d);
+                    else
+                        d0[k] = fminf(d0[k], d);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            if (k < p.bits)
+                out[s_row[k] + j] = (int8_t)convert_8i(__fmul_rn(__fsub_rn(d1[k], d0[k]), inv_n0));
+    }
+}
+
 } // namespace
+
+cudaError_t demap_table_launch(const TableDemapLaunch& p, cudaStream_t stream)
+{
+    if (p.frames <= 0)
+        return cudaSuccess;
+    dim3 grid((p.n_syms + 255) / 256, p.frames);
+    demap_table_kernel<<<grid, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
 
 cudaError_t snr_launch(const SnrLaunch& p, cudaStream_t stream)
 {

@@ -76,6 +76,16 @@ struct DemapLaunch {
 };
 cudaError_t demap_launch(const DemapLaunch& p, cudaStream_t stream);
 
+struct TableDemapLaunch {
+    const float* iq;     // [frames][n_syms][2]
+    const float* n0;     // [frames]
+    int8_t* llr;         // [frames][n_syms * bits]
+    const float* points; // device: [2^bits][2], index = the symbol's bits, first bit = MSB
+    const int* row_off;  // device: [bits], bit k of symbol j -> llr[row_off[k] + j]
+    int frames, n_syms, bits;
+};
+cudaError_t demap_table_launch(const TableDemapLaunch& p, cudaStream_t stream);
+
 struct SnrLaunch {
     const float* iq;   // [frames][n_syms][2]
     const int8_t* llr; // null: slice the symbols; else [frames][N] posterior LLRs (codeword order)

@@ -75,6 +75,8 @@ _SIGS = {
     "dvbs2b200_demap_dev": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, _P]),
     "dvbs2b200_fec_decode": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "dvbs2b200_fec_decode_dev": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "dvbs2b200_demap_table": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, _P, _P]),
+    "dvbs2b200_demap_table_dev": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, _P, _P, _P]),
     "dvbs2b200_mixed_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, _P, _P, _P]),
     "dvbs2b200_mixed_destroy": (None, [_P]),
     "dvbs2b200_mixed_code_info": (C.c_int, [_P, C.c_int, C.POINTER(CodeInfo)]),
@@ -261,6 +263,25 @@ class Code:
         _check(lib().dvbs2b200_fec_decode(self._h, constellation, _ptr(iq), _ptr(n0), _ptr(llr), F, max_trials,
                                           term_group, msg.ctypes.data, trials.ctypes.data, corr.ctypes.data))
         return msg, trials, corr
+
+    def demap_table(self, points, row_offsets, iq, n0):
+        """Max-log soft demap against a constellation table [2^bits, 2]; bit k of symbol j -> llr[row_offsets[k] + j]."""
+        points = _np(points, np.float32).reshape(-1, 2)
+        bits = int(points.shape[0]).bit_length() - 1
+        rows = _np(row_offsets, np.int32)
+        iq = _np(iq, np.float32).reshape(-1, self.N // bits, 2)
+        F = iq.shape[0]
+        n0 = _np(np.broadcast_to(np.asarray(n0, dtype=np.float32), (F,)), np.float32)
+        llr = np.empty((F, self.N), dtype=np.int8)
+        _check(lib().dvbs2b200_demap_table(self._h, bits, points.ctypes.data, rows.ctypes.data, iq.ctypes.data, F,
+                                           n0.ctypes.data, llr.ctypes.data))
+        return llr
+
+    def demap_table_dev(self, points, row_offsets, d_iq, frames, d_n0, d_llr, stream):
+        points = _np(points, np.float32).reshape(-1, 2)
+        bits = int(points.shape[0]).bit_length() - 1
+        rows = _np(row_offsets, np.int32)
+        _check(lib().dvbs2b200_demap_table_dev(self._h, bits, points.ctypes.data, rows.ctypes.data, d_iq, frames, d_n0, d_llr, stream))
 
     def estimate_snr(self, constellation, iq, llr_post=None):
         """Linear Es/N0 per frame: from sliced symbols, or from posterior LLR signs when given."""

@@ -143,6 +143,21 @@ int dvbs2b200_demap(dvbs2b200_code* h, int constellation, const float* iq, int f
 int dvbs2b200_demap_dev(dvbs2b200_code* h, int constellation, const float* d_iq, int frames,
                         const float* d_n0, int8_t* d_llr, void* stream);
 
+/* ---- table-driven soft demapper: 16APSK, 32APSK, any constellation of up to 32 points ------------- */
+/* NOT a replacement of reference code: gr-dvbs2rx demaps QPSK and 8PSK only and throws "Unsupported
+ * constellation" otherwise (lib/xfecframe_demapper_cb_impl.cc:70-72), as dvbs2b200_demap does.  This entry
+ * point is SURVEY 8f rank 3, defined by this library:
+ *   llr_k = ( min_{s: bit k = 1} |y - s|^2 - min_{s: bit k = 0} |y - s|^2 ) / N0   (max-log; positive = bit 0,
+ *   the convention of lib/qpsk.h:208-214; rounded to nearest even, saturated to int8)
+ *   points      [2^bits][2] constellation, index = the symbol's bits with the first bit as MSB (host pointer)
+ *   row_offsets [bits]: bit k of symbol j goes to llr[f][row_offsets[k] + j] -- the DVB-S2 bit interleaver read
+ *               back (n_ldpc/bits rows, `bits` columns), whatever the column order of the MODCOD (host pointer)
+ * dvbs2rx_b200.apsk (Python) builds the EN 302 307-1 16APSK / 32APSK tables for a ring ratio. */
+int dvbs2b200_demap_table(dvbs2b200_code* h, int bits, const float* points, const int* row_offsets,
+                          const float* iq, int frames, const float* n0, int8_t* llr);
+int dvbs2b200_demap_table_dev(dvbs2b200_code* h, int bits, const float* points, const int* row_offsets,
+                              const float* d_iq, int frames, const float* d_n0, int8_t* d_llr, void* stream);
+
 /* ---- mixed-MODCOD (VCM/ACM) batches ------------------------------------------------------------ */
 /* The reference's blocks are CCM: one MODCOD per block instance (lib/ldpc_decoder_bb_impl.cc:79-368), a VCM
  * receiver runs one chain per MODCOD.  A dvbs2b200_mixed holds one code handle per MODCOD of the stream on

@@ -236,3 +236,43 @@ def test_mixed_modcod_batch_matches_per_code_oracle(gpu, oracle):
     assert np.array_equal(tr, np.array(want_tr)) and np.array_equal(co, np.array(want_co))
     assert (tr >= 0).sum() >= len(order) - 2  # nearly everything converges at these SNRs
     mixed.close()
+
+
+def test_table_demapper_16apsk_32apsk(gpu, oracle):
+    """dvbs2b200_demap_table (no reference counterpart): within 1 LSB of a float64 max-log model, QPSK through
+    it equals the reference-exact QPSK demapper, and 16APSK / 32APSK frames decode through LDPC + BCH."""
+    d = gpu
+    from dvbs2rx_b200 import apsk, vectors
+    rng = np.random.default_rng(61)
+    # QPSK as a table: same bytes as dvbs2b200_demap (lib/qpsk.h:208-214) away from rounding ties
+    code = d.Code(0, 0, d.C2_3)
+    a = np.float32(np.sqrt(0.5))
+    qpsk = np.array([[a, a], [a, -a], [-a, a], [-a, -a]], dtype=np.float32)
+    msg, cw, info = vectors.encode_frames(0, 0, d.C2_3, 3, rng)
+    iq, n0 = vectors.awgn(vectors.map_symbols(cw, d.MOD_QPSK, d.C2_3), 4.0, rng)
+    offs = np.array([0, 1], dtype=np.int32)  # QPSK is not interleaved: bit k of symbol j at 2j + k
+    ref = code.demap(d.MOD_QPSK, iq, n0).astype(np.int16)
+    got = code.demap_table(qpsk, apsk.row_offsets(16200, 2), iq, n0).astype(np.int16)
+    got = np.stack([got[:, :8100], got[:, 8100:]], axis=2).reshape(3, 16200)  # rows -> interleaved pairs
+    assert np.abs(got - ref).max() <= 1 and (got != ref).mean() < 0.01
+    del offs
+    for name, pts, fs, rate, esn0 in (("16APSK 2/3 short", apsk.points_16apsk(apsk.GAMMA_16APSK["C2_3"]), 0, d.C2_3, 10.5),
+                                      ("32APSK 9/10 normal", apsk.points_32apsk(*apsk.GAMMA_32APSK["C9_10"]), 1, d.C9_10, 17.5)):
+        assert abs(float((pts.astype(np.float64) ** 2).sum(axis=1).mean()) - 1.0) < 1e-6
+        assert len({(round(float(x), 5), round(float(y), 5)) for x, y in pts}) == pts.shape[0]  # distinct points
+        code = d.Code(0, fs, rate)
+        bits = int(pts.shape[0]).bit_length() - 1
+        F = 4
+        msg, cw, info = vectors.encode_frames(0, fs, rate, F, rng)
+        offs = apsk.row_offsets(info.n_ldpc, bits)
+        iq, n0 = vectors.awgn(apsk.map_bits(cw, pts, offs), esn0, rng)
+        llr = code.demap_table(pts, offs, iq, n0)
+        model = apsk.maxlog_llr(iq, pts, offs, n0)
+        want = np.clip(np.rint(model), -128, 127)
+        assert np.abs(llr.astype(np.float64) - want).max() <= 1, name
+        assert (llr.astype(np.float64) != want).mean() < 0.01, name
+        out, trials, corr = code.fec_decode(llr=llr, max_trials=25)
+        assert (trials >= 0).all() and np.array_equal(out, msg), name
+        code.close()
+    with pytest.raises(d.Dvbs2Error):
+        d.Code(0, 1, d.C1_2).demap_table(np.zeros((64, 2), np.float32), np.zeros(6, np.int32), np.zeros((1, 10800, 2), np.float32), 1.0)
