@@ -162,6 +162,22 @@ def run_reference(args):
     }))
 
 
+def cpu_reference_ldpc_rate(table_name, llr, trials, threads=None):
+    """Frames/s of the reference's own AVX2 LDPC decoder (oracle/_ref) on `llr`, one decoder instance per host
+    thread; None where oracle/_ref is not built.  The one CPU leg other measurement tools (tools/sweep_configs.py)
+    go through, so that nothing outside tests/, smoke() and this file touches oracle/."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    if not os.path.exists(oracle_lib.REF_PATH):
+        return None
+    ref = oracle_lib.Ref()
+    threads = threads or (os.cpu_count() or 1)
+    F = min(32 * threads, llr.shape[0] // 32 * 32)
+    ref.ldpc_decode_mt(table_name, llr[:F], trials, threads)
+    post, ret, t1 = ref.ldpc_decode_mt(table_name, llr[:F], trials, threads)
+    return dict(ldpc_frames_per_s=F / t1, threads=threads, frames=F)
+
+
 # --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------

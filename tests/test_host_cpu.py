@@ -176,3 +176,24 @@ def test_mixed_batch_sharding(built):
             assert i1 - i0 == sizes_in[lo:hi].sum() and o1 - o0 == sizes_out[lo:hi].sum()
             prev_hi, prev_in, prev_out = hi, i1, o1
         assert prev_hi == 37 and prev_in == sizes_in.sum() and prev_out == sizes_out.sum()
+
+
+def test_apsk_tables_and_model(built):
+    """dvbs2rx_b200.apsk: unit-energy, distinct points; the float64 max-log model reduces to the QPSK formula."""
+    from dvbs2rx_b200 import apsk, vectors
+    for pts in [apsk.points_16apsk(g) for g in apsk.GAMMA_16APSK.values()] + \
+               [apsk.points_32apsk(*g) for g in apsk.GAMMA_32APSK.values()]:
+        assert abs(float((pts.astype(np.float64) ** 2).sum(axis=1).mean()) - 1.0) < 1e-6
+        assert len({(round(float(x), 5), round(float(y), 5)) for x, y in pts}) == pts.shape[0]
+    assert apsk.row_offsets(64800, 4).tolist() == [0, 16200, 32400, 48600]
+    assert apsk.row_offsets(64800, 3, (2, 1, 0)).tolist() == [43200, 21600, 0]
+    rng = np.random.default_rng(1)
+    a = np.float32(np.sqrt(0.5))
+    qpsk = np.array([[a, a], [a, -a], [-a, a], [-a, -a]], dtype=np.float32)
+    bits = rng.integers(0, 2, size=(2, 64), dtype=np.uint8)
+    offs = apsk.row_offsets(64, 2)
+    iq = apsk.map_bits(bits, qpsk, offs) + rng.normal(0, 0.3, size=(2, 32, 2)).astype(np.float32)
+    n0 = 0.18
+    model = apsk.maxlog_llr(iq, qpsk, offs, n0)
+    want = np.concatenate([iq[:, :, 0], iq[:, :, 1]], axis=1).astype(np.float64) * (2 * np.sqrt(2.0) / n0)
+    assert np.allclose(model, want, rtol=1e-5, atol=1e-5)

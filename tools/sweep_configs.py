@@ -19,7 +19,6 @@ import __graft_entry__ as ge  # noqa: E402
 ge.build()
 import dvbs2rx_b200 as d  # noqa: E402
 from dvbs2rx_b200 import vectors  # noqa: E402
-import oracle_lib  # noqa: E402
 
 HBM = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
     os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
@@ -41,15 +40,10 @@ def timed(fn, reps=5, warm=2):
 
 
 def cpu_ref(info, llr, trials, fs):
-    if not os.path.exists(oracle_lib.REF_PATH):
-        return None
-    ref = oracle_lib.Ref()
-    threads = os.cpu_count() or 1
-    F = 32 * threads
+    # the reference CPU leg lives in bench.py (the only measurement code that may execute oracle/)
+    import bench
     name = d.lib().dvbs2b200_table_name(info.table).decode()
-    post, ret, t1 = ref.ldpc_decode_mt(name, llr[:F], trials, threads)
-    post, ret, t1 = ref.ldpc_decode_mt(name, llr[:F], trials, threads)
-    return dict(ldpc_frames_per_s=F / t1, threads=threads, frames=F)
+    return bench.cpu_reference_ldpc_rate(name, llr, trials)
 
 
 CONFIGS = [
