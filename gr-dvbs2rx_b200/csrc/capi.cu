@@ -300,8 +300,11 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
         CU(cudaMemcpy(host.data(), h->d_prof.p, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         if (FILE* f = fopen(prof_path, "w")) {
             static const char* names[13] = { "load", "syndrome_pass", "pair_steps", "narrow_runs", "wide_steps", "iteration_end",
-                                             "output", "total", "split_barrier_wait", "split_chain", "split_handover", "split_warp_levels",
-                                             "split_pre" };
+                                             "output", "total",
+                                             // split steps.  level form: barrier wait, node work, hand-over, warp-levels, prologue;
+                                             // chain form: records + barrier, warp 0's walk, wait for the other walkers, levels, -
+                                             "split_wait_or_records", "split_node_work", "split_handover_or_wait", "split_levels",
+                                             "split_prologue" };
             for (int k = 0; k < 13; ++k) {
                 double sum = 0;
                 for (int b = 0; b < grid; ++b)

@@ -6,6 +6,7 @@
     python tools/run_one.py bb    C1_2 1 0 0 8192        # descrambler + deheader alone on clean BBFRAMEs
     python tools/run_one.py snr   C3_5 1 6.2 0 2664      # SNR estimate (8PSK for 3/5, else QPSK) + demap
     python tools/run_one.py mixed C1_2 1 0 25 5000       # five MODCODs interleaved in one batch (host API)
+    python tools/run_one.py apsk  C9_10 1 17.5 0 2664    # table-driven demapper (32APSK for 8/9, 9/10, else 16APSK)
 
 Prints device time per pass (CUDA events) and the derived rates; not the bench line."""
 import os
@@ -101,6 +102,25 @@ elif what == "mixed":
     t = (time.perf_counter() - t0) / reps
     print("mixed: %d frames of %d MODCODs, %.1f ms per batch through the host API, %.0f frames/s, %.0f%% converged" % (
         order.size, len(modcods), t * 1e3, order.size / t, 100.0 * (tr >= 0).mean()))
+elif what == "apsk":
+    # table-driven demapper: 16APSK for 2/3, 3/4, 4/5, 5/6 (bits = 4), 32APSK for 8/9, 9/10 (bits = 5)
+    from dvbs2rx_b200 import apsk
+    if rate_name in ("C8_9", "C9_10"):
+        pts = apsk.points_32apsk(*apsk.GAMMA_32APSK[rate_name])
+    else:
+        pts = apsk.points_16apsk(apsk.GAMMA_16APSK[rate_name])
+    bits = int(pts.shape[0]).bit_length() - 1
+    offs = apsk.row_offsets(info.n_ldpc, bits)
+    msg, cw, info2 = vectors.encode_frames(0, fs, rate, 8, rng)
+    iq, n0 = vectors.awgn(apsk.map_bits(cw, pts, offs), esn0, rng)
+    iq = np.tile(iq, (F // 8 + 1, 1, 1))[:F]
+    d_iq = torch.from_numpy(iq).to(dev)
+    d_n0 = torch.full((F,), float(n0), dtype=torch.float32, device=dev)
+    d_llr = torch.empty((F, info.n_ldpc), dtype=torch.int8, device=dev)
+    t = timed(lambda: code.demap_table_dev(pts, offs, d_iq.data_ptr(), F, d_n0.data_ptr(), d_llr.data_ptr(), stream), reps=10)
+    nbytes = F * (info.n_ldpc // bits) * 8 + F * info.n_ldpc
+    print("apsk %s (%d points): %.1f us per %d frames, %.0f GB/s of symbols in + LLRs out, %.1f M symbols/ms" % (
+        rate_name, pts.shape[0], t * 1e6, F, nbytes / t / 1e9, F * (info.n_ldpc // bits) / t / 1e9))
 elif what == "bb":
     up, bb = bb_stream(F)
     d_bb = torch.from_numpy(bbf.scramble(bb)).to(dev)
