@@ -86,6 +86,7 @@ struct dvbs2b200_code {
     // BB layer: descrambling sequence, deheader stream state, per-call scratch, TS output staging
     DevBuf d_prbs, d_bbstate, d_bbrec, d_bbplan, d_ts;
     DevBuf d_points; // table-driven demapper: constellation [32][2] floats + row offsets [5] ints
+    std::vector<uint8_t> points_cache; // what d_points holds (the table is re-sent only when it changes)
     bool bb_ready = false;
 };
 
@@ -1249,14 +1250,21 @@ int dvbs2b200_demap_table_dev(dvbs2b200_code* h, int bits, const float* points, 
     int rc = h->d_points.ensure(32 * 2 * sizeof(float) + 8 * sizeof(int));
     if (rc)
         return rc;
-    // the table rides along with the call (320 bytes); staged copies are ordered on the caller's stream
+    // the table (288 bytes) is sent when it differs from what the device already holds; the copy is ordered on
+    // the caller's stream and its source is a local, hence the synchronisation on a change
     float hp[64] = { 0 };
     int hr[8] = { 0 };
     memcpy(hp, points, sizeof(float) * 2 * ((size_t)1 << bits));
     memcpy(hr, row_offsets, sizeof(int) * bits);
-    CU(cudaMemcpyAsync(h->d_points.p, hp, sizeof(hp), cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync((uint8_t*)h->d_points.p + sizeof(hp), hr, sizeof(hr), cudaMemcpyHostToDevice, s));
-    CU(cudaStreamSynchronize(s)); // hp / hr are locals
+    std::vector<uint8_t> want(sizeof(hp) + sizeof(hr));
+    memcpy(want.data(), hp, sizeof(hp));
+    memcpy(want.data() + sizeof(hp), hr, sizeof(hr));
+    if (want != h->points_cache) {
+        CU(cudaStreamSynchronize(s)); // an earlier launch on this stream may still be reading the old table
+        CU(cudaMemcpyAsync(h->d_points.p, want.data(), want.size(), cudaMemcpyHostToDevice, s));
+        CU(cudaStreamSynchronize(s));
+        h->points_cache.swap(want);
+    }
     TableDemapLaunch p;
     memset(&p, 0, sizeof(p));
     p.points = (const float*)h->d_points.p;
