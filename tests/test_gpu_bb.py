@@ -109,3 +109,47 @@ def test_chain_soft_input_to_ts_packets(gpu, oracle):
     o_msg, _ = oracle.bch_decode(oracle.bch(fs, info.t, info.nbch), oracle.pack_hard(o_post, info.nbch))
     assert np.array_equal(ts3, oracle.bbdeheader(info.kbch).work(oracle.bb_descramble(o_msg, info.kbch)))
     code.close()
+
+
+def test_deheader_random_headers_match_oracle(gpu, oracle):
+    """Random BBHEADERs (valid CRC, arbitrary DFL / SYNCD, some broken) over random payloads: every state
+    transition class of the deheader's frame-to-frame recurrence, in random order, over several calls.
+    The product's parallel scan must agree with the oracle's frame-by-frame walk byte for byte."""
+    d = gpu
+    kbch, kb = 3072, 384  # QPSK 1/4 short: the smallest BBFRAME, many frames per packet boundary pattern
+    code = d.Code(0, 0, d.C1_4)
+    assert code.kbch == kbch
+    max_df = kb - 10
+    for seed in range(6):
+        rng = np.random.default_rng(100 + seed)
+        n = 700
+        bb = rng.integers(0, 256, size=(n, kb), dtype=np.uint8)
+        pending = 0  # bytes of a cut packet a well-formed stream would announce
+        for f in range(n):
+            r = rng.random()
+            df = int(rng.choice([max_df, max_df, max_df, 188 * (max_df // 188), 100, 0, 187, 188, 8 * int(rng.integers(0, max_df // 8 + 1)) // 8]))
+            df = min(df, max_df)
+            if r < 0.55:    # continues the stream
+                syncd = (188 - pending) % 188
+            elif r < 0.75:  # random but valid SYNCD
+                syncd = int(rng.integers(0, df + 1)) if df else 0
+            elif r < 0.85:  # SYNCD == DFL (the re-synchronisation edge)
+                syncd = df
+            else:
+                syncd = int(rng.integers(0, 400))
+            hdr = bbf.bbheader(df * 8, min(syncd, 8191) * 8).copy()
+            if r > 0.93:
+                hdr[int(rng.integers(0, 10))] ^= 1 << int(rng.integers(0, 8))  # CRC failure
+            elif r > 0.90:
+                hdr = bbf.bbheader(df * 8 + 4, 0).copy()                      # DFL not a multiple of 8
+            bb[f, :10] = hdr
+            pending = (pending + df) % 188
+        o = oracle.bbdeheader(kbch)
+        code.bb_reset()
+        cuts = sorted(rng.choice(np.arange(1, n), size=3, replace=False).tolist())
+        for lo, hi in zip([0] + cuts, cuts + [n]):
+            want = o.work(bb[lo:hi])
+            got = code.bb_deheader(bb[lo:hi], scrambled=False)
+            assert got.size == want.size and np.array_equal(got, want), (seed, lo, hi)
+        assert code.bb_counters() == o.counters(), seed
+    code.close()
