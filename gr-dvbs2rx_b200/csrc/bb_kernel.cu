@@ -421,4 +421,22 @@ cudaError_t bb_deheader_launch(const BbLaunch& p, cudaStream_t stream)
     return cudaGetLastError();
 }
 
+// Forces the module that holds these kernels to be loaded now (CUDA loads lazily at the first launch, and that
+// load can wait for the device to go idle -- which never happens while the persistent LDPC kernel of the
+// streaming path is resident and waiting for input that the blocked host thread has yet to send).
+cudaError_t bb_preload()
+{
+    cudaFuncAttributes a;
+    cudaError_t e;
+    if ((e = cudaFuncGetAttributes(&a, bb_descramble_kernel)) != cudaSuccess)
+        return e;
+    if ((e = cudaFuncGetAttributes(&a, bb_header_kernel)) != cudaSuccess)
+        return e;
+    if ((e = cudaFuncGetAttributes(&a, bb_scan_kernel)) != cudaSuccess)
+        return e;
+    if ((e = cudaFuncGetAttributes(&a, bb_ts_kernel)) != cudaSuccess)
+        return e;
+    return cudaSuccess;
+}
+
 } // namespace dvbs2b200

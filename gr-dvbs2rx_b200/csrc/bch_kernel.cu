@@ -262,4 +262,16 @@ cudaError_t bch_launch(const BchLaunch& p, cudaStream_t stream)
     return cudaGetLastError();
 }
 
+// Forces the module that holds these kernels to be loaded now (CUDA loads lazily at the first launch, and that
+// load can wait for the device to go idle -- which never happens while the persistent LDPC kernel of the
+// streaming path is resident and waiting for input that the blocked host thread has yet to send).
+cudaError_t bch_preload()
+{
+    cudaFuncAttributes a;
+    cudaError_t e;
+    if ((e = cudaFuncGetAttributes(&a, bch_decode_kernel)) != cudaSuccess)
+        return e;
+    return cudaSuccess;
+}
+
 } // namespace dvbs2b200

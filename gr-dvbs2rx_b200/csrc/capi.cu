@@ -8,6 +8,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/dvbs2_b200.h"
@@ -66,6 +67,45 @@ struct DevBuf {
     }
 };
 
+struct HostBuf { // pinned host memory
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap)
+            return DVBS2B200_OK;
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            g_err = std::string("cudaHostAlloc: ") + cudaGetErrorString(e);
+            return DVBS2B200_ENOMEM;
+        }
+        cap = bytes;
+        return DVBS2B200_OK;
+    }
+    void release()
+    {
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// true if the driver can DMA straight from / to this host pointer (pinned or registered memory)
+bool host_ptr_is_pinned(const void* ptr)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
 } // namespace
 
 struct dvbs2b200_code {
@@ -88,6 +128,16 @@ struct dvbs2b200_code {
     DevBuf d_points; // table-driven demapper: constellation [32][2] floats + row offsets [5] ints
     std::vector<uint8_t> points_cache; // what d_points holds (the table is re-sent only when it changes)
     bool bb_ready = false;
+    // The handle's device scratch (check-node state, intermediates, BB state) is shared by all its calls: work
+    // issued on one stream must not overlap work issued on another.  Every call records ev_last on the stream
+    // it used; a call on a different stream waits for it first.
+    cudaStream_t last_stream = nullptr;
+    cudaEvent_t ev_last = nullptr;
+    bool ev_valid = false;
+    // pinned staging for pageable host buffers: a ring of input slots, one output area, the arrival counters
+    HostBuf h_ring, h_out, h_cnt;
+    cudaEvent_t ev_slot[3] = { nullptr, nullptr, nullptr };
+    DevBuf d_err; // error word of the streaming LDPC launch (input never arrived)
 };
 
 // A set of codes on one device for mixed-MODCOD (VCM/ACM) batches.
@@ -100,6 +150,11 @@ struct dvbs2b200_mixed {
         DevBuf d_in_off, d_out_off, d_pos, d_stage_in, d_stage_out, d_tr, d_co;
     };
     std::vector<PerCode> per;
+};
+
+// One code on several devices of this process: a batch is split into contiguous frame ranges, one per device.
+struct dvbs2b200_multi {
+    std::vector<dvbs2b200_code*> codes; // one handle (tables, streams, scratch) per device
 };
 
 namespace {
@@ -119,10 +174,10 @@ void info_from_header(const BlobHeader& h, dvbs2b200_code_info* info)
     info->gf_m = h.gf_m;
 }
 
-int create_from_blob(dvbs2b200_code** out, int device, std::vector<uint8_t>&& blob)
+int create_from_blob(dvbs2b200_code** out, int device, std::vector<uint8_t>&& blob, bool validated = false)
 {
     std::string err;
-    if (!validate_blob(blob.data(), blob.size(), err))
+    if (!validated && !validate_blob(blob.data(), blob.size(), err))
         return fail(DVBS2B200_EINVAL, err);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -157,6 +212,9 @@ int create_from_blob(dvbs2b200_code** out, int device, std::vector<uint8_t>&& bl
     // run on non-blocking streams that do not order against it
     if ((e = cudaDeviceSynchronize()) != cudaSuccess)
         return bail(cuda_fail(e, "cudaDeviceSynchronize(tables)"));
+    if ((e = bch_preload()) != cudaSuccess || (e = bb_preload()) != cudaSuccess || (e = demap_preload()) != cudaSuccess ||
+        (e = mixed_preload()) != cudaSuccess)
+        return bail(cuda_fail(e, "kernel preload"));
     h->ldpc_smem = ldpc_smem_bytes(h->hdr.N, h->hdr.smem_bytes, h->hdr.chain_scratch != 0, nullptr);
     auto ctas_per_sm = h->hdr.split_steps ? ldpc_ctas_per_sm_split : ldpc_ctas_per_sm_wavefront;
     if (h->hdr.max_cnt <= 28 && h->ldpc_smem <= (size_t)h->smem_optin)
@@ -196,6 +254,29 @@ struct DeviceGuard {
     }
 };
 
+// Stream ordering of a handle's calls (see dvbs2b200_code::ev_last).
+struct StreamOrder {
+    dvbs2b200_code* h;
+    cudaStream_t s;
+    StreamOrder(dvbs2b200_code* h_, cudaStream_t s_) : h(h_), s(s_)
+    {
+        if (h->ev_valid && h->last_stream != s)
+            cudaStreamWaitEvent(s, h->ev_last, 0);
+    }
+    ~StreamOrder()
+    {
+        if (!h->ev_last && cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming) != cudaSuccess) {
+            h->ev_last = nullptr;
+            cudaStreamSynchronize(s); // no event to order by: fall back to completing the work
+            h->ev_valid = false;
+            return;
+        }
+        cudaEventRecord(h->ev_last, s);
+        h->last_stream = s;
+        h->ev_valid = true;
+    }
+};
+
 int ldpc_out_bytes(const BlobHeader& h, int output_mode) { return (output_mode ? h.kldpc_out : h.N) / 8; }
 
 // grid size: persistent CTAs, as many as are resident at once; in group mode a multiple of the group
@@ -210,7 +291,7 @@ int ldpc_grid(const dvbs2b200_code* h, int frames, int group, bool tmem)
 
 int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials, int term_group, int output_mode,
              uint8_t* d_hard, int8_t* d_llr_post, int32_t* d_trials_left, cudaStream_t stream,
-             const unsigned int* d_ready = nullptr, int ready_chunk = 0)
+             const unsigned int* d_ready = nullptr, int ready_chunk = 0, unsigned int* d_err = nullptr)
 {
     const BlobHeader& hd = h->hdr;
     if (frames < 0 || max_trials < 0)
@@ -224,7 +305,7 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
     if (term_group > 1 && frames % term_group)
         return fail(DVBS2B200_EINVAL, "frames must be a multiple of term_group");
     if (hd.max_cnt > 28)
-        return fail(DVBS2B200_EUNSUPPORTED, "check-node degree above 30");
+        return fail(DVBS2B200_EUNSUPPORTED, "more than 28 data links per check node");
     if (h->ldpc_ctas <= 0)
         return fail(DVBS2B200_ECUDA, "LDPC kernel cannot be resident on this device (shared memory / registers)");
     if (term_group > 1 && h->sm_count * h->ldpc_ctas < term_group)
@@ -261,6 +342,7 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
     p.llr = d_llr;
     p.ready = d_ready;
     p.ready_chunk = ready_chunk;
+    p.err = d_err;
     p.frames = frames;
     p.max_trials = max_trials;
     p.group = group;
@@ -418,6 +500,8 @@ int demap_dev(dvbs2b200_code* h, int constellation, const float* d_iq, int frame
         return DVBS2B200_OK;
     if (!d_iq || !d_n0 || !d_llr)
         return fail(DVBS2B200_EINVAL, "null buffer");
+    if (((uintptr_t)d_iq & 15) || ((uintptr_t)d_llr & 3)) // 128-bit symbol loads, 32-bit packed LLR stores
+        return fail(DVBS2B200_EINVAL, "symbol buffer must be 16-byte aligned and the LLR buffer 4-byte aligned");
     DemapLaunch p;
     memset(&p, 0, sizeof(p));
     p.n_syms = hd.N / bits;
@@ -691,11 +775,21 @@ void dvbs2b200_code_destroy(dvbs2b200_code* h)
     if (!h)
         return;
     DeviceGuard g(h->device);
-    if (h->stream)
-        cudaStreamSynchronize(h->stream);
+    if (h->ev_valid && h->ev_last)
+        cudaEventSynchronize(h->ev_last); // asynchronous calls on a caller's stream may still use the scratch
+    for (cudaStream_t st : { h->stream, h->s_in, h->s_out })
+        if (st)
+            cudaStreamSynchronize(st);
     for (DevBuf* b : { &h->d_in, &h->d_mid, &h->d_out, &h->d_post, &h->d_i32a, &h->d_i32b, &h->d_n0, &h->d_llr, &h->d_sync, &h->d_scratch, &h->d_flag, &h->d_prof,
-                       &h->d_prbs, &h->d_bbstate, &h->d_bbrec, &h->d_bbplan, &h->d_ts, &h->d_points })
+                       &h->d_prbs, &h->d_bbstate, &h->d_bbrec, &h->d_bbplan, &h->d_ts, &h->d_points, &h->d_err })
         b->release();
+    for (HostBuf* b : { &h->h_ring, &h->h_out, &h->h_cnt })
+        b->release();
+    for (cudaEvent_t& e : h->ev_slot)
+        if (e)
+            cudaEventDestroy(e);
+    if (h->ev_last)
+        cudaEventDestroy(h->ev_last);
     if (h->d_blob)
         cudaFree(h->d_blob);
     for (cudaStream_t st : { h->stream, h->s_in, h->s_out })
@@ -722,6 +816,7 @@ int dvbs2b200_ldpc_decode_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames
     if (!h)
         return fail(DVBS2B200_EINVAL, "null handle");
     DeviceGuard g(h->device);
+    StreamOrder so(h, (cudaStream_t)stream);
     return ldpc_dev(h, d_llr, frames, max_trials, term_group, output_mode, d_hard, d_llr_post, d_trials_left,
                     (cudaStream_t)stream);
 }
@@ -738,6 +833,7 @@ int dvbs2b200_ldpc_decode(dvbs2b200_code* h, const int8_t* llr, int frames, int 
     if (!llr)
         return fail(DVBS2B200_EINVAL, "llr is null");
     DeviceGuard g(h->device);
+    StreamOrder so(h, h->stream);
     const BlobHeader& hd = h->hdr;
     const size_t in_bytes = (size_t)frames * hd.N;
     const size_t out_bytes = (size_t)frames * ldpc_out_bytes(hd, output_mode);
@@ -774,6 +870,7 @@ int dvbs2b200_bch_decode_dev(dvbs2b200_code* h, const uint8_t* d_cw, int frames,
     if (!h)
         return fail(DVBS2B200_EINVAL, "null handle");
     DeviceGuard g(h->device);
+    StreamOrder so(h, (cudaStream_t)stream);
     return bch_dev(h, d_cw, h->hdr.nbch / 8, frames, d_msg, d_corrections, (cudaStream_t)stream);
 }
 
@@ -788,6 +885,7 @@ int dvbs2b200_bch_decode(dvbs2b200_code* h, const uint8_t* cw, int frames, uint8
     if (!cw || !msg)
         return fail(DVBS2B200_EINVAL, "null buffer");
     DeviceGuard g(h->device);
+    StreamOrder so(h, h->stream);
     const BlobHeader& hd = h->hdr;
     const size_t in_bytes = (size_t)frames * (hd.nbch / 8), out_bytes = (size_t)frames * (hd.kbch / 8);
     int rc;
@@ -813,6 +911,7 @@ int dvbs2b200_demap_dev(dvbs2b200_code* h, int constellation, const float* d_iq,
     if (!h)
         return fail(DVBS2B200_EINVAL, "null handle");
     DeviceGuard g(h->device);
+    StreamOrder so(h, (cudaStream_t)stream);
     return demap_dev(h, constellation, d_iq, frames, d_n0, d_llr, (cudaStream_t)stream);
 }
 
@@ -830,6 +929,7 @@ int dvbs2b200_demap(dvbs2b200_code* h, int constellation, const float* iq, int f
     if (!iq || !n0 || !llr)
         return fail(DVBS2B200_EINVAL, "null buffer");
     DeviceGuard g(h->device);
+    StreamOrder so(h, h->stream);
     const BlobHeader& hd = h->hdr;
     const size_t iq_bytes = (size_t)frames * (hd.N / bits) * 8, llr_bytes = (size_t)frames * hd.N;
     int rc;
@@ -854,7 +954,7 @@ namespace {
 int fec_dev_range(dvbs2b200_code* h, int constellation, const float* d_iq, const float* d_n0, const int8_t* d_llr,
                   int f0, int nf, int max_trials, int term_group, uint8_t* d_llr_scratch, uint8_t* d_mid,
                   uint8_t* d_msg, int32_t* d_trials_left, int32_t* d_corrections, cudaStream_t s,
-                  const unsigned int* d_ready = nullptr, int ready_chunk = 0)
+                  const unsigned int* d_ready = nullptr, int ready_chunk = 0, unsigned int* d_err = nullptr)
 {
     const BlobHeader& hd = h->hdr;
     int rc;
@@ -873,7 +973,7 @@ int fec_dev_range(dvbs2b200_code* h, int constellation, const float* d_iq, const
     const int mid_stride = hd.kldpc_out / 8; // OM_MESSAGE: BCH codeword bytes
     uint8_t* mid = d_mid + (size_t)f0 * mid_stride;
     if ((rc = ldpc_dev(h, llr, nf, max_trials, term_group, /*OM_MESSAGE*/ 1, mid, nullptr,
-                       d_trials_left ? d_trials_left + f0 : nullptr, s, d_ready, ready_chunk)))
+                       d_trials_left ? d_trials_left + f0 : nullptr, s, d_ready, ready_chunk, d_err)))
         return rc;
     return bch_dev(h, mid, mid_stride, nf, d_msg + (size_t)f0 * (hd.kbch / 8),
                    d_corrections ? d_corrections + f0 : nullptr, s);
@@ -897,6 +997,7 @@ int dvbs2b200_fec_decode_dev(dvbs2b200_code* h, int constellation, const float* 
     if (d_iq && !d_n0)
         return fail(DVBS2B200_EINVAL, "n0 is null");
     DeviceGuard g(h->device);
+    StreamOrder so(h, (cudaStream_t)stream);
     const BlobHeader& hd = h->hdr;
     int rc;
     if (d_iq && (rc = h->d_llr.ensure((size_t)frames * hd.N)))
@@ -922,6 +1023,7 @@ int dvbs2b200_fec_decode(dvbs2b200_code* h, int constellation, const float* iq, 
     if (iq && !n0)
         return fail(DVBS2B200_EINVAL, "n0 is null");
     DeviceGuard g(h->device);
+    StreamOrder so(h, h->stream);
     const BlobHeader& hd = h->hdr;
     const int bits = iq ? bits_per_symbol(constellation) : 0;
     if (iq && !bits)
@@ -940,58 +1042,105 @@ int dvbs2b200_fec_decode(dvbs2b200_code* h, int constellation, const float* iq, 
     if (iq && ((rc = h->d_n0.ensure((size_t)frames * 4)) || (rc = h->d_llr.ensure((size_t)frames * hd.N))))
         return rc;
     if (!iq && term_group <= 1) {
-        // Streaming path (LLR input): ONE persistent LDPC launch over the whole batch.  The input is
-        // copied in chunks on the copy-in stream, each followed by a one-thread kernel that bumps an
-        // arrival counter; a CTA waits on that counter before it loads a frame.  Host->device transfer
-        // and decoding overlap without cutting the batch into separate launches.
+        // Streaming path (LLR input): ONE persistent LDPC launch over the whole batch, issued FIRST; the input
+        // then arrives in chunks on the copy-in stream, each followed by a 4-byte DMA copy that publishes the
+        // number of chunks that have landed; a CTA waits on that counter before it loads a frame.  The
+        // counter is advanced by the copy engine, not by a kernel, so the resident, spinning CTAs cannot starve
+        // it of SM resources; a CTA that waits for more than ~17 s sets the error word and the call fails.
+        // Pageable host buffers (GNU Radio's ring buffers) are staged chunk by chunk through a ring of pinned
+        // slots while the device decodes the chunks that are already there.
         const int sc = std::max(32, h->sm_count); // frames per arrival flag
         const int n_sc = (frames + sc - 1) / sc;
-        if ((rc = h->d_flag.ensure(16)))
+        const bool in_pinned = host_ptr_is_pinned(llr), out_pinned = host_ptr_is_pinned(msg);
+        constexpr int kSlots = 3;
+        if ((rc = h->d_flag.ensure(16)) || (rc = h->d_err.ensure(16)) || (rc = h->h_cnt.ensure((size_t)n_sc * sizeof(unsigned int))))
             return rc;
+        if (!in_pinned && (rc = h->h_ring.ensure((size_t)kSlots * sc * in_stride)))
+            return rc;
+        const size_t out_bytes_al = ((size_t)frames * out_stride + 15) & ~(size_t)15;
+        if (!out_pinned && (rc = h->h_out.ensure(out_bytes_al + (size_t)frames * 8)))
+            return rc;
+        for (int k = 0; k < kSlots; ++k)
+            if (!h->ev_slot[k])
+                CU(cudaEventCreateWithFlags(&h->ev_slot[k], cudaEventDisableTiming));
+        unsigned int* cnt = (unsigned int*)h->h_cnt.p;
+        for (int c = 0; c < n_sc; ++c)
+            cnt[c] = (unsigned int)(c + 1);
         cudaEvent_t ev_zero = nullptr;
         cudaError_t e;
         unsigned int* flag = (unsigned int*)h->d_flag.p;
         auto bail = [&](cudaError_t err, const char* what) {
+            // let the resident kernel out: everything has "arrived" (its results are discarded with the error)
+            unsigned int all = 0xffffffffu;
+            cudaMemcpyAsync(flag, &all, 4, cudaMemcpyHostToDevice, h->s_in);
             cudaDeviceSynchronize();
             if (ev_zero)
                 cudaEventDestroy(ev_zero);
             return cuda_fail(err, what);
         };
         if ((e = cudaMemsetAsync(flag, 0, 4, h->s_in)) != cudaSuccess)
-            return bail(e, "cudaMemsetAsync(flag)");
+            return cuda_fail(e, "cudaMemsetAsync(flag)");
+        if ((e = cudaMemsetAsync(h->d_err.p, 0, 4, h->s_in)) != cudaSuccess)
+            return cuda_fail(e, "cudaMemsetAsync(err)");
         if ((e = cudaEventCreateWithFlags(&ev_zero, cudaEventDisableTiming)) != cudaSuccess)
-            return bail(e, "cudaEventCreate");
-        if ((e = cudaEventRecord(ev_zero, h->s_in)) != cudaSuccess)
-            return bail(e, "cudaEventRecord");
-        for (int c = 0; c < n_sc; ++c) {
-            const int f0 = c * sc, nf = std::min(sc, frames - f0);
-            if ((e = cudaMemcpyAsync((uint8_t*)h->d_in.p + (size_t)f0 * in_stride, (const uint8_t*)llr + (size_t)f0 * in_stride,
-                                     (size_t)nf * in_stride, cudaMemcpyHostToDevice, h->s_in)) != cudaSuccess)
-                return bail(e, "cudaMemcpyAsync(llr chunk)");
-            if ((e = flag_launch(flag, (unsigned int)(c + 1), h->s_in)) != cudaSuccess)
-                return bail(e, "flag_launch");
+            return cuda_fail(e, "cudaEventCreate");
+        if ((e = cudaEventRecord(ev_zero, h->s_in)) != cudaSuccess || (e = cudaStreamWaitEvent(h->stream, ev_zero, 0)) != cudaSuccess) {
+            cudaEventDestroy(ev_zero);
+            return cuda_fail(e, "cudaEventRecord");
         }
-        if ((e = cudaStreamWaitEvent(h->stream, ev_zero, 0)) != cudaSuccess)
-            return bail(e, "cudaStreamWaitEvent");
         rc = fec_dev_range(h, constellation, nullptr, nullptr, (const int8_t*)h->d_in.p, 0, frames, max_trials, term_group,
                            (uint8_t*)h->d_llr.p, (uint8_t*)h->d_mid.p, (uint8_t*)h->d_out.p, (int32_t*)h->d_i32a.p,
-                           (int32_t*)h->d_i32b.p, h->stream, flag, sc);
+                           (int32_t*)h->d_i32b.p, h->stream, flag, sc, (unsigned int*)h->d_err.p);
         if (rc) {
-            cudaDeviceSynchronize();
-            cudaEventDestroy(ev_zero);
+            bail(cudaSuccess, "launch");
             return rc;
         }
-        if ((e = cudaMemcpyAsync(msg, h->d_out.p, (size_t)frames * out_stride, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess)
+        for (int c = 0; c < n_sc; ++c) {
+            const int f0 = c * sc, nf = std::min(sc, frames - f0);
+            const uint8_t* src = (const uint8_t*)llr + (size_t)f0 * in_stride;
+            if (!in_pinned) {
+                const int slot = c % kSlots;
+                uint8_t* stage = (uint8_t*)h->h_ring.p + (size_t)slot * sc * in_stride;
+                if (c >= kSlots && (e = cudaEventSynchronize(h->ev_slot[slot])) != cudaSuccess)
+                    return bail(e, "cudaEventSynchronize(slot)");
+                memcpy(stage, src, (size_t)nf * in_stride);
+                src = stage;
+            }
+            if ((e = cudaMemcpyAsync((uint8_t*)h->d_in.p + (size_t)f0 * in_stride, src, (size_t)nf * in_stride, cudaMemcpyHostToDevice,
+                                     h->s_in)) != cudaSuccess)
+                return bail(e, "cudaMemcpyAsync(llr chunk)");
+            if (!in_pinned && (e = cudaEventRecord(h->ev_slot[c % kSlots], h->s_in)) != cudaSuccess)
+                return bail(e, "cudaEventRecord(slot)");
+            if ((e = cudaMemcpyAsync(flag, &cnt[c], 4, cudaMemcpyHostToDevice, h->s_in)) != cudaSuccess)
+                return bail(e, "cudaMemcpyAsync(arrival counter)");
+        }
+        uint8_t* o_msg = out_pinned ? msg : (uint8_t*)h->h_out.p;
+        int32_t* o_tr = out_pinned ? trials_left : (int32_t*)((uint8_t*)h->h_out.p + out_bytes_al);
+        int32_t* o_co = out_pinned ? corrections : o_tr + frames;
+        if ((e = cudaMemcpyAsync(o_msg, h->d_out.p, (size_t)frames * out_stride, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess)
             return bail(e, "cudaMemcpyAsync(msg)");
-        if (trials_left && (e = cudaMemcpyAsync(trials_left, h->d_i32a.p, (size_t)frames * 4, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess)
+        if (trials_left && (e = cudaMemcpyAsync(o_tr, h->d_i32a.p, (size_t)frames * 4, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess)
             return bail(e, "cudaMemcpyAsync(trials)");
-        if (corrections && (e = cudaMemcpyAsync(corrections, h->d_i32b.p, (size_t)frames * 4, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess)
+        if (corrections && (e = cudaMemcpyAsync(o_co, h->d_i32b.p, (size_t)frames * 4, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess)
             return bail(e, "cudaMemcpyAsync(corrections)");
-        if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess)
-            return bail(e, "cudaStreamSynchronize");
+        unsigned int err_word = 0;
+        if ((e = cudaMemcpyAsync(&cnt[0], h->d_err.p, 4, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess) // cnt[0] is free by now
+            return bail(e, "cudaMemcpyAsync(err)");
         if ((e = cudaStreamSynchronize(h->s_in)) != cudaSuccess)
             return bail(e, "cudaStreamSynchronize");
+        if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess)
+            return bail(e, "cudaStreamSynchronize");
+        err_word = cnt[0];
         cudaEventDestroy(ev_zero);
+        if (err_word)
+            return fail(DVBS2B200_ECUDA, "LDPC kernel gave up waiting for its input (host-to-device copy never arrived)");
+        if (!out_pinned) {
+            memcpy(msg, o_msg, (size_t)frames * out_stride);
+            if (trials_left)
+                memcpy(trials_left, o_tr, (size_t)frames * 4);
+            if (corrections)
+                memcpy(corrections, o_co, (size_t)frames * 4);
+        }
         return DVBS2B200_OK;
     }
     // Pipeline (symbol input / group mode): the batch is cut into chunks of full waves of resident CTAs; chunk c+1 is copied in
@@ -1087,6 +1236,35 @@ int dvbs2b200_mixed_create(dvbs2b200_mixed** out, int device, int n_codes, const
     return DVBS2B200_OK;
 }
 
+int dvbs2b200_mixed_create_from_tables(dvbs2b200_mixed** out, int device, int n_codes, const void* const* blobs, const size_t* sizes)
+{
+    if (!out || n_codes <= 0 || n_codes > 255 || !blobs || !sizes)
+        return fail(DVBS2B200_EINVAL, "bad argument");
+    *out = nullptr;
+    dvbs2b200_mixed* m = new (std::nothrow) dvbs2b200_mixed();
+    if (!m)
+        return fail(DVBS2B200_ENOMEM, "out of host memory");
+    m->device = device;
+    for (int c = 0; c < n_codes; ++c) {
+        dvbs2b200_code* h = nullptr;
+        int rc = dvbs2b200_code_create_from_tables(&h, device, blobs[c], sizes[c]);
+        if (rc) {
+            dvbs2b200_mixed_destroy(m);
+            return rc;
+        }
+        m->codes.push_back(h);
+    }
+    m->per.resize(n_codes);
+    DeviceGuard g(device);
+    cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        dvbs2b200_mixed_destroy(m);
+        return cuda_fail(e, "cudaStreamCreate");
+    }
+    *out = m;
+    return DVBS2B200_OK;
+}
+
 void dvbs2b200_mixed_destroy(dvbs2b200_mixed* m)
 {
     if (!m)
@@ -1115,27 +1293,20 @@ int dvbs2b200_mixed_code_info(const dvbs2b200_mixed* m, int code, dvbs2b200_code
     return dvbs2b200_code_info_get(m->codes[code], info);
 }
 
-int dvbs2b200_mixed_fec_decode(dvbs2b200_mixed* m, int frames, const uint8_t* code_id, const int8_t* llr, int max_trials,
-                               uint8_t* msg, int32_t* trials_left, int32_t* corrections)
+} // extern "C"
+
+namespace {
+// The batch with its input and outputs in device memory: bucket the frames by code (host), gather each bucket,
+// decode it on its code's stream, scatter the results back; `stream` waits for every bucket before it goes on.
+int mixed_dev(dvbs2b200_mixed* m, int frames, const uint8_t* code_id, const int8_t* d_llr, int max_trials, uint8_t* d_msg,
+              int32_t* d_trials_left, int32_t* d_corrections, cudaStream_t stream, unsigned long long in_total_expect)
 {
-    if (!m)
-        return fail(DVBS2B200_EINVAL, "null handle");
-    if (frames < 0)
-        return fail(DVBS2B200_EINVAL, "negative frames");
-    if (frames == 0)
-        return DVBS2B200_OK;
-    if (!code_id || !llr || !msg)
-        return fail(DVBS2B200_EINVAL, "null buffer");
-    DeviceGuard g(m->device);
     const int nc = (int)m->codes.size();
-    // bucket the frames by code: byte offsets into the concatenated input / output, positions in the batch
     std::vector<std::vector<unsigned long long>> in_off(nc), out_off(nc);
     std::vector<std::vector<int32_t>> pos(nc);
     unsigned long long in_total = 0, out_total = 0;
     for (int f = 0; f < frames; ++f) {
         const int c = code_id[f];
-        if (c >= nc)
-            return fail(DVBS2B200_EINVAL, "code_id out of range");
         const BlobHeader& hd = m->codes[c]->hdr;
         in_off[c].push_back(in_total);
         out_off[c].push_back(out_total);
@@ -1143,10 +1314,19 @@ int dvbs2b200_mixed_fec_decode(dvbs2b200_mixed* m, int frames, const uint8_t* co
         in_total += (unsigned long long)hd.N;
         out_total += (unsigned long long)hd.kbch / 8;
     }
+    (void)in_total_expect;
     int rc;
-    if ((rc = m->d_in.ensure(in_total)) || (rc = m->d_out.ensure(out_total)) || (rc = m->d_tr.ensure((size_t)frames * 4)) ||
-        (rc = m->d_co.ensure((size_t)frames * 4)))
-        return rc;
+    // status words are always produced on the device (the scatter kernel writes them); the caller may not want them
+    if (!d_trials_left) {
+        if ((rc = m->d_tr.ensure((size_t)frames * 4)))
+            return rc;
+        d_trials_left = (int32_t*)m->d_tr.p;
+    }
+    if (!d_corrections) {
+        if ((rc = m->d_co.ensure((size_t)frames * 4)))
+            return rc;
+        d_corrections = (int32_t*)m->d_co.p;
+    }
     cudaEvent_t ev_in = nullptr;
     std::vector<cudaEvent_t> ev_done(nc, nullptr);
     auto cleanup = [&]() {
@@ -1165,9 +1345,8 @@ int dvbs2b200_mixed_fec_decode(dvbs2b200_mixed* m, int frames, const uint8_t* co
             return cuda_fail(e__, #call);        \
         }                                        \
     } while (0)
-    CUM(cudaMemcpyAsync(m->d_in.p, llr, in_total, cudaMemcpyHostToDevice, m->stream));
     CUM(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
-    CUM(cudaEventRecord(ev_in, m->stream));
+    CUM(cudaEventRecord(ev_in, stream));
     for (int c = 0; c < nc; ++c) {
         const int n = (int)pos[c].size();
         if (n == 0)
@@ -1184,11 +1363,12 @@ int dvbs2b200_mixed_fec_decode(dvbs2b200_mixed* m, int frames, const uint8_t* co
             return rc;
         }
         cudaStream_t s = h->stream; // every code decodes on its own stream: the codes of a batch overlap
+        // (pageable sources: the copies are staged before the calls return, the vectors may go out of scope)
         CUM(cudaMemcpyAsync(pc.d_in_off.p, in_off[c].data(), (size_t)n * 8, cudaMemcpyHostToDevice, s));
         CUM(cudaMemcpyAsync(pc.d_out_off.p, out_off[c].data(), (size_t)n * 8, cudaMemcpyHostToDevice, s));
         CUM(cudaMemcpyAsync(pc.d_pos.p, pos[c].data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
         CUM(cudaStreamWaitEvent(s, ev_in, 0));
-        CUM(gather_launch((const uint8_t*)m->d_in.p, (const unsigned long long*)pc.d_in_off.p, (uint8_t*)pc.d_stage_in.p, hd.N, n, s));
+        CUM(gather_launch((const uint8_t*)d_llr, (const unsigned long long*)pc.d_in_off.p, (uint8_t*)pc.d_stage_in.p, hd.N, n, s));
         rc = dvbs2b200_fec_decode_dev(h, 0, nullptr, nullptr, (const int8_t*)pc.d_stage_in.p, n, max_trials, 0, (uint8_t*)pc.d_stage_out.p,
                                       (int32_t*)pc.d_tr.p, (int32_t*)pc.d_co.p, s);
         if (rc) {
@@ -1196,22 +1376,92 @@ int dvbs2b200_mixed_fec_decode(dvbs2b200_mixed* m, int frames, const uint8_t* co
             cleanup();
             return rc;
         }
-        CUM(scatter_launch((const uint8_t*)pc.d_stage_out.p, (const unsigned long long*)pc.d_out_off.p, (uint8_t*)m->d_out.p, kb, n,
-                           (const int32_t*)pc.d_tr.p, (const int32_t*)pc.d_co.p, (const int32_t*)pc.d_pos.p, (int32_t*)m->d_tr.p,
-                           (int32_t*)m->d_co.p, s));
+        CUM(scatter_launch((const uint8_t*)pc.d_stage_out.p, (const unsigned long long*)pc.d_out_off.p, d_msg, kb, n,
+                           (const int32_t*)pc.d_tr.p, (const int32_t*)pc.d_co.p, (const int32_t*)pc.d_pos.p, d_trials_left,
+                           d_corrections, s));
         h->launches += 2;
         CUM(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
         CUM(cudaEventRecord(ev_done[c], s));
-        CUM(cudaStreamWaitEvent(m->stream, ev_done[c], 0));
+        CUM(cudaStreamWaitEvent(stream, ev_done[c], 0));
     }
-    CUM(cudaMemcpyAsync(msg, m->d_out.p, out_total, cudaMemcpyDeviceToHost, m->stream));
-    if (trials_left)
-        CUM(cudaMemcpyAsync(trials_left, m->d_tr.p, (size_t)frames * 4, cudaMemcpyDeviceToHost, m->stream));
-    if (corrections)
-        CUM(cudaMemcpyAsync(corrections, m->d_co.p, (size_t)frames * 4, cudaMemcpyDeviceToHost, m->stream));
-    CUM(cudaStreamSynchronize(m->stream));
 #undef CUM
     cleanup();
+    return DVBS2B200_OK;
+}
+
+int mixed_sizes(const dvbs2b200_mixed* m, int frames, const uint8_t* code_id, unsigned long long* in_total, unsigned long long* out_total)
+{
+    const int nc = (int)m->codes.size();
+    *in_total = *out_total = 0;
+    for (int f = 0; f < frames; ++f) {
+        if (code_id[f] >= nc)
+            return fail(DVBS2B200_EINVAL, "code_id out of range");
+        const BlobHeader& hd = m->codes[code_id[f]]->hdr;
+        *in_total += (unsigned long long)hd.N;
+        *out_total += (unsigned long long)hd.kbch / 8;
+    }
+    return DVBS2B200_OK;
+}
+} // namespace
+
+extern "C" {
+
+int dvbs2b200_mixed_fec_decode_dev(dvbs2b200_mixed* m, int frames, const uint8_t* code_id, const int8_t* d_llr, int max_trials,
+                                   uint8_t* d_msg, int32_t* d_trials_left, int32_t* d_corrections, void* stream)
+{
+    if (!m)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    if (frames < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames");
+    if (frames == 0)
+        return DVBS2B200_OK;
+    if (!code_id || !d_llr || !d_msg)
+        return fail(DVBS2B200_EINVAL, "null buffer");
+    DeviceGuard g(m->device);
+    unsigned long long in_total, out_total;
+    int rc = mixed_sizes(m, frames, code_id, &in_total, &out_total);
+    if (rc)
+        return rc;
+    return mixed_dev(m, frames, code_id, d_llr, max_trials, d_msg, d_trials_left, d_corrections, (cudaStream_t)stream, in_total);
+}
+
+int dvbs2b200_mixed_fec_decode(dvbs2b200_mixed* m, int frames, const uint8_t* code_id, const int8_t* llr, int max_trials,
+                               uint8_t* msg, int32_t* trials_left, int32_t* corrections)
+{
+    if (!m)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    if (frames < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames");
+    if (frames == 0)
+        return DVBS2B200_OK;
+    if (!code_id || !llr || !msg)
+        return fail(DVBS2B200_EINVAL, "null buffer");
+    DeviceGuard g(m->device);
+    unsigned long long in_total, out_total;
+    int rc = mixed_sizes(m, frames, code_id, &in_total, &out_total);
+    if (rc)
+        return rc;
+    if ((rc = m->d_in.ensure(in_total)) || (rc = m->d_out.ensure(out_total)) || (rc = m->d_tr.ensure((size_t)frames * 4)) ||
+        (rc = m->d_co.ensure((size_t)frames * 4)))
+        return rc;
+    auto bail = [&](cudaError_t e, const char* what) {
+        cudaDeviceSynchronize();
+        return cuda_fail(e, what);
+    };
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(m->d_in.p, llr, in_total, cudaMemcpyHostToDevice, m->stream)) != cudaSuccess)
+        return bail(e, "cudaMemcpyAsync(llr)");
+    if ((rc = mixed_dev(m, frames, code_id, (const int8_t*)m->d_in.p, max_trials, (uint8_t*)m->d_out.p, (int32_t*)m->d_tr.p,
+                        (int32_t*)m->d_co.p, m->stream, in_total)))
+        return rc;
+    if ((e = cudaMemcpyAsync(msg, m->d_out.p, out_total, cudaMemcpyDeviceToHost, m->stream)) != cudaSuccess)
+        return bail(e, "cudaMemcpyAsync(msg)");
+    if (trials_left && (e = cudaMemcpyAsync(trials_left, m->d_tr.p, (size_t)frames * 4, cudaMemcpyDeviceToHost, m->stream)) != cudaSuccess)
+        return bail(e, "cudaMemcpyAsync(trials)");
+    if (corrections && (e = cudaMemcpyAsync(corrections, m->d_co.p, (size_t)frames * 4, cudaMemcpyDeviceToHost, m->stream)) != cudaSuccess)
+        return bail(e, "cudaMemcpyAsync(corrections)");
+    if ((e = cudaStreamSynchronize(m->stream)) != cudaSuccess)
+        return bail(e, "cudaStreamSynchronize");
     return DVBS2B200_OK;
 }
 
@@ -1246,6 +1496,7 @@ int dvbs2b200_demap_table_dev(dvbs2b200_code* h, int bits, const float* points, 
         if (row_offsets[k] < 0 || row_offsets[k] + n_syms > hd.N)
             return fail(DVBS2B200_EINVAL, "row offset out of range");
     DeviceGuard g(h->device);
+    StreamOrder so(h, (cudaStream_t)stream);
     cudaStream_t s = (cudaStream_t)stream;
     int rc = h->d_points.ensure(32 * 2 * sizeof(float) + 8 * sizeof(int));
     if (rc)
@@ -1298,6 +1549,7 @@ int dvbs2b200_demap_table(dvbs2b200_code* h, int bits, const float* points, cons
     if (!iq || !n0 || !llr)
         return fail(DVBS2B200_EINVAL, "null buffer");
     DeviceGuard g(h->device);
+    StreamOrder so(h, h->stream);
     const BlobHeader& hd = h->hdr;
     if (hd.N % bits)
         return fail(DVBS2B200_EINVAL, "frame length is not a multiple of the bits per symbol");
@@ -1324,6 +1576,7 @@ int dvbs2b200_estimate_snr_dev(dvbs2b200_code* h, int constellation, const float
     if (!h)
         return fail(DVBS2B200_EINVAL, "null handle");
     DeviceGuard g(h->device);
+    StreamOrder so(h, (cudaStream_t)stream);
     return snr_dev(h, constellation, d_iq, d_llr_post, frames, d_snr_lin, (cudaStream_t)stream);
 }
 
@@ -1342,6 +1595,7 @@ int dvbs2b200_estimate_snr(dvbs2b200_code* h, int constellation, const float* iq
     if (!iq || !snr_lin)
         return fail(DVBS2B200_EINVAL, "null buffer");
     DeviceGuard g(h->device);
+    StreamOrder so(h, h->stream);
     const BlobHeader& hd = h->hdr;
     const size_t iq_bytes = (size_t)frames * (hd.N / bits) * 8, llr_bytes = (size_t)frames * hd.N;
     int rc;
@@ -1367,6 +1621,7 @@ int dvbs2b200_bb_descramble_dev(dvbs2b200_code* h, const uint8_t* d_in, int fram
     if (!h)
         return fail(DVBS2B200_EINVAL, "null handle");
     DeviceGuard g(h->device);
+    StreamOrder so(h, (cudaStream_t)stream);
     return bb_descramble_dev(h, d_in, frames, d_out, (cudaStream_t)stream);
 }
 
@@ -1381,6 +1636,7 @@ int dvbs2b200_bb_descramble(dvbs2b200_code* h, const uint8_t* in, int frames, ui
     if (!in || !out)
         return fail(DVBS2B200_EINVAL, "null buffer");
     DeviceGuard g(h->device);
+    StreamOrder so(h, h->stream);
     const size_t bytes = (size_t)frames * (h->hdr.kbch / 8);
     int rc;
     if ((rc = h->d_mid.ensure(bytes)) || (rc = h->d_out.ensure(bytes)))
@@ -1405,6 +1661,7 @@ int dvbs2b200_bb_deheader_dev(dvbs2b200_code* h, const uint8_t* d_bbframes, int 
     if (!h)
         return fail(DVBS2B200_EINVAL, "null handle");
     DeviceGuard g(h->device);
+    StreamOrder so(h, (cudaStream_t)stream);
     return bb_deheader_dev(h, d_bbframes, frames, scrambled, d_ts, ts_cap, (cudaStream_t)stream);
 }
 
@@ -1422,6 +1679,7 @@ int dvbs2b200_bb_deheader(dvbs2b200_code* h, const uint8_t* bbframes, int frames
     if (!bbframes || !ts)
         return fail(DVBS2B200_EINVAL, "null buffer");
     DeviceGuard g(h->device);
+    StreamOrder so(h, h->stream);
     const size_t bytes = (size_t)frames * (h->hdr.kbch / 8);
     const size_t cap = std::min(ts_cap, bb_ts_capacity(h->hdr, frames));
     int rc;
@@ -1443,6 +1701,7 @@ int dvbs2b200_bb_produced_dev(dvbs2b200_code* h, void* stream, size_t* ts_bytes)
     if (rc)
         return rc;
     unsigned long long produced = 0;
+    StreamOrder so(h, (cudaStream_t)stream);
     CU(cudaMemcpyAsync(&produced, &((BbState*)h->d_bbstate.p)->produced, sizeof(produced), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU(cudaStreamSynchronize((cudaStream_t)stream));
     *ts_bytes = (size_t)produced;
@@ -1457,6 +1716,7 @@ int dvbs2b200_bb_reset(dvbs2b200_code* h)
     int rc = bb_ensure(h);
     if (rc)
         return rc;
+    StreamOrder so(h, h->stream); // after whatever an earlier call left running on another stream
     CU(cudaMemsetAsync(h->d_bbstate.p, 0, sizeof(BbState), h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return DVBS2B200_OK;
@@ -1492,6 +1752,7 @@ int dvbs2b200_fec_decode_ts_dev(dvbs2b200_code* h, int constellation, const floa
     if (frames == 0)
         return DVBS2B200_OK;
     DeviceGuard g(h->device);
+    StreamOrder so(h, (cudaStream_t)stream);
     int rc;
     if ((rc = h->d_out.ensure((size_t)frames * (h->hdr.kbch / 8))))
         return rc;
@@ -1518,6 +1779,7 @@ int dvbs2b200_fec_decode_ts(dvbs2b200_code* h, int constellation, const float* i
     if (iq && !n0)
         return fail(DVBS2B200_EINVAL, "n0 is null");
     DeviceGuard g(h->device);
+    StreamOrder so(h, h->stream);
     const BlobHeader& hd = h->hdr;
     const int bits = iq ? bits_per_symbol(constellation) : 0;
     if (iq && !bits)
@@ -1545,6 +1807,106 @@ int dvbs2b200_fec_decode_ts(dvbs2b200_code* h, int constellation, const float* i
     if (corrections)
         CU(cudaMemcpyAsync(corrections, h->d_i32b.p, (size_t)frames * 4, cudaMemcpyDeviceToHost, s));
     return bb_fetch_ts(h, (const uint8_t*)h->d_ts.p, ts, cap, ts_bytes, s);
+}
+
+// ---- one code on several devices of one process -----------------------------------------------------------
+int dvbs2b200_multi_create(dvbs2b200_multi** out, const int* devices, int n_devices, int standard, int framesize, int rate)
+{
+    if (!out || !devices || n_devices <= 0 || n_devices > 64)
+        return fail(DVBS2B200_EINVAL, "bad argument");
+    *out = nullptr;
+    // the tables are built ONCE on the host; every device gets the same blob with one host-to-device copy
+    std::vector<uint8_t> blob;
+    std::string err;
+    if (!build_blob(standard, framesize, rate, blob, err))
+        return fail(DVBS2B200_EUNSUPPORTED, err);
+    dvbs2b200_multi* m = new (std::nothrow) dvbs2b200_multi();
+    if (!m)
+        return fail(DVBS2B200_ENOMEM, "out of host memory");
+    for (int i = 0; i < n_devices; ++i) {
+        dvbs2b200_code* h = nullptr;
+        int rc = create_from_blob(&h, devices[i], std::vector<uint8_t>(blob), /*validated=*/true);
+        if (rc) {
+            dvbs2b200_multi_destroy(m);
+            return rc;
+        }
+        m->codes.push_back(h);
+    }
+    *out = m;
+    return DVBS2B200_OK;
+}
+
+void dvbs2b200_multi_destroy(dvbs2b200_multi* m)
+{
+    if (!m)
+        return;
+    for (dvbs2b200_code* h : m->codes)
+        dvbs2b200_code_destroy(h);
+    delete m;
+}
+
+int dvbs2b200_multi_device_count(const dvbs2b200_multi* m) { return m ? (int)m->codes.size() : 0; }
+
+dvbs2b200_code* dvbs2b200_multi_code(dvbs2b200_multi* m, int index)
+{
+    return (m && index >= 0 && index < (int)m->codes.size()) ? m->codes[index] : nullptr;
+}
+
+int dvbs2b200_multi_shard(const dvbs2b200_multi* m, int frames, int index, int* first, int* count)
+{
+    if (!m || !first || !count || index < 0 || index >= (int)m->codes.size() || frames < 0)
+        return fail(DVBS2B200_EINVAL, "bad argument");
+    // contiguous ranges whose boundaries fall on multiples of 32 frames, so that a batch-coupled termination
+    // group (16 / 32 frames, lib/ldpc_decoder/layered_decoder.hh:153) never straddles two devices
+    const int world = (int)m->codes.size();
+    const int units = (frames + 31) / 32, per = units / world, extra = units % world;
+    const int lo = index * per + std::min(index, extra), hi = lo + per + (index < extra ? 1 : 0);
+    *first = std::min(lo * 32, frames);
+    *count = std::min(hi * 32, frames) - *first;
+    return DVBS2B200_OK;
+}
+
+int dvbs2b200_multi_fec_decode(dvbs2b200_multi* m, int constellation, const float* iq, const float* n0, const int8_t* llr, int frames,
+                               int max_trials, int term_group, uint8_t* msg, int32_t* trials_left, int32_t* corrections)
+{
+    if (!m || m->codes.empty())
+        return fail(DVBS2B200_EINVAL, "null handle");
+    if (frames < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames");
+    if (frames == 0)
+        return DVBS2B200_OK;
+    if (!msg || (!iq && !llr))
+        return fail(DVBS2B200_EINVAL, "null buffer");
+    const int world = (int)m->codes.size();
+    const BlobHeader& hd = m->codes[0]->hdr;
+    const int bits = iq ? bits_per_symbol(constellation) : 0;
+    if (iq && !bits)
+        return fail(DVBS2B200_EUNSUPPORTED, "Unsupported constellation");
+    std::vector<int> rcs(world, DVBS2B200_OK);
+    std::vector<std::string> errs(world);
+    // one worker per device: the caller stays one thread; the workers stage and launch concurrently
+    auto work = [&](int i) {
+        int f0 = 0, nf = 0;
+        dvbs2b200_multi_shard(m, frames, i, &f0, &nf);
+        if (nf == 0)
+            return;
+        rcs[i] = dvbs2b200_fec_decode(m->codes[i], constellation, iq ? iq + (size_t)f0 * (hd.N / bits) * 2 : nullptr, n0 ? n0 + f0 : nullptr,
+                                      llr ? llr + (size_t)f0 * hd.N : nullptr, nf, max_trials, term_group,
+                                      msg + (size_t)f0 * (hd.kbch / 8), trials_left ? trials_left + f0 : nullptr,
+                                      corrections ? corrections + f0 : nullptr);
+        if (rcs[i])
+            errs[i] = g_err; // thread-local in the worker
+    };
+    std::vector<std::thread> th;
+    for (int i = 1; i < world; ++i)
+        th.emplace_back(work, i);
+    work(0);
+    for (auto& t : th)
+        t.join();
+    for (int i = 0; i < world; ++i)
+        if (rcs[i])
+            return fail(rcs[i], "device " + std::to_string(m->codes[i]->device) + ": " + errs[i]);
+    return DVBS2B200_OK;
 }
 
 } // extern "C"

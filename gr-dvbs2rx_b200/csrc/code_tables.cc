@@ -524,9 +524,21 @@ bool validate_blob(const void* blob, size_t size, std::string& err)
               h.n_steps_total > 0 && h.n_steps_total <= h.steps_per_iter &&
               (size_t)h.antilog_off + gfn <= size && (size_t)h.log_off + gfn <= size &&
               (h.msg_words == 1 || h.msg_words == 2) && h.gf_m >= 14 && h.gf_m <= 16;
-    if (!ok)
+    if (!ok) {
         err = "table blob failed consistency checks";
-    return ok;
+        return false;
+    }
+    // The kernels trust every index in the blob (step list, circulants, work lists).  The blob is a pure
+    // function of (standard, framesize, rate): rebuild it (a few ms) and compare -- anything corrupted,
+    // truncated or built by another version of the library is rejected here instead of faulting on the device.
+    std::vector<uint8_t> again;
+    std::string berr;
+    if (!build_blob(h.standard, h.framesize, h.rate, again, berr) || again.size() != size ||
+        memcmp(again.data(), blob, size) != 0) {
+        err = "table blob does not match the tables this library builds for its (standard, framesize, rate)";
+        return false;
+    }
+    return true;
 }
 
 } // namespace dvbs2b200

@@ -235,4 +235,22 @@ cudaError_t demap_launch(const DemapLaunch& p, cudaStream_t stream)
     return cudaGetLastError();
 }
 
+// Forces the module that holds these kernels to be loaded now (CUDA loads lazily at the first launch, and that
+// load can wait for the device to go idle -- which never happens while the persistent LDPC kernel of the
+// streaming path is resident and waiting for input that the blocked host thread has yet to send).
+cudaError_t demap_preload()
+{
+    cudaFuncAttributes a;
+    cudaError_t e;
+    if ((e = cudaFuncGetAttributes(&a, demap_table_kernel)) != cudaSuccess)
+        return e;
+    if ((e = cudaFuncGetAttributes(&a, snr_kernel)) != cudaSuccess)
+        return e;
+    if ((e = cudaFuncGetAttributes(&a, demap_qpsk_kernel)) != cudaSuccess)
+        return e;
+    if ((e = cudaFuncGetAttributes(&a, demap_8psk_kernel)) != cudaSuccess)
+        return e;
+    return cudaSuccess;
+}
+
 } // namespace dvbs2b200

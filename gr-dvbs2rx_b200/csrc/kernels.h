@@ -23,6 +23,7 @@ struct LdpcLaunch {
     // streaming input: *ready counts the chunks of ready_chunk frames that have arrived (null: all there)
     const unsigned int* ready;
     int ready_chunk;
+    unsigned int* err; // set to 1 by a CTA that gave up waiting on *ready (null: not reported)
     int frames;
     int max_trials;
     int group;           // 0 per-frame termination, else frames per coupled group
@@ -139,7 +140,11 @@ cudaError_t gather_launch(const uint8_t* src, const unsigned long long* off, uin
 cudaError_t scatter_launch(const uint8_t* src, const unsigned long long* off, uint8_t* dst, int bytes, int frames, const int32_t* v0,
                            const int32_t* v1, const int32_t* pos, int32_t* o0, int32_t* o1, cudaStream_t stream);
 
-// one-thread kernel that publishes `value` at *flag (stream-ordered after the copies before it)
-cudaError_t flag_launch(unsigned int* flag, unsigned int value, cudaStream_t stream);
+
+// load the kernels of a translation unit ahead of their first launch (see bch_kernel.cu)
+cudaError_t bch_preload();
+cudaError_t bb_preload();
+cudaError_t demap_preload();
+cudaError_t mixed_preload();
 
 } // namespace dvbs2b200

@@ -1286,6 +1286,7 @@ __global__ void __launch_bounds__(kLdpcThreads, (DVBS2_LEGACY_WAVEFRONT || CNT_M
     uint2* const rec = reinterpret_cast<uint2*>(smem + p.smem_rec_off); // node scratch of chain-form split steps
     (void)rec;
     __shared__ int s_group_bad;
+    __shared__ int s_abort;
     __shared__ uint32_t s_tmem_base;
     __shared__ int s_progress; // split steps: highest level of the current layer known to be complete
 
@@ -1349,11 +1350,23 @@ __global__ void __launch_bounds__(kLdpcThreads, (DVBS2_LEGACY_WAVEFRONT || CNT_M
         if (p.ready) {
             if (tid == 0) {
                 const unsigned int need = (unsigned int)(f / p.ready_chunk) + 1u;
-                while (*reinterpret_cast<const volatile unsigned int*>(p.ready) < need)
+                const long long t0 = clock64();
+                int gave_up = 0;
+                while (*reinterpret_cast<const volatile unsigned int*>(p.ready) < need) {
                     __nanosleep(500);
+                    if (clock64() - t0 > (1ll << 35)) { // ~17 s: the copy is not coming (host-side failure)
+                        gave_up = 1;
+                        break;
+                    }
+                }
+                if (gave_up && p.err)
+                    atomicExch(p.err, 1u);
+                s_abort = gave_up;
                 __threadfence();
             }
             __syncthreads();
+            if (s_abort)
+                break;
         }
         // ---- soft input: HBM -> shared memory, into the pair-interleaved order --------------------
         {
@@ -1645,20 +1658,6 @@ int occupancy_one(size_t smem)
 } // namespace
 
 #if !DVBS2_LEGACY_WAVEFRONT // shared helpers live in one of the two translation units
-namespace {
-__global__ void flag_kernel(unsigned int* flag, unsigned int value)
-{
-    __threadfence();
-    *reinterpret_cast<volatile unsigned int*>(flag) = value;
-}
-} // namespace
-
-cudaError_t flag_launch(unsigned int* flag, unsigned int value, cudaStream_t stream)
-{
-    flag_kernel<<<1, 1, 0, stream>>>(flag, value);
-    return cudaGetLastError();
-}
-
 size_t ldpc_smem_bytes(int N, uint32_t tab_bytes, bool chain_scratch, LdpcLaunch* p)
 {
     size_t off = ((size_t)N + 15) & ~(size_t)15;

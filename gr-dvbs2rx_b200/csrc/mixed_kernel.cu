@@ -68,4 +68,18 @@ cudaError_t scatter_launch(const uint8_t* src, const unsigned long long* off, ui
     return cudaGetLastError();
 }
 
+// Forces the module that holds these kernels to be loaded now (CUDA loads lazily at the first launch, and that
+// load can wait for the device to go idle -- which never happens while the persistent LDPC kernel of the
+// streaming path is resident and waiting for input that the blocked host thread has yet to send).
+cudaError_t mixed_preload()
+{
+    cudaFuncAttributes a;
+    cudaError_t e;
+    if ((e = cudaFuncGetAttributes(&a, gather_kernel)) != cudaSuccess)
+        return e;
+    if ((e = cudaFuncGetAttributes(&a, scatter_kernel)) != cudaSuccess)
+        return e;
+    return cudaSuccess;
+}
+
 } // namespace dvbs2b200

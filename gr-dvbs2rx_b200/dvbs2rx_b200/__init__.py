@@ -82,6 +82,14 @@ _SIGS = {
     "dvbs2b200_mixed_code_info": (C.c_int, [_P, C.c_int, C.POINTER(CodeInfo)]),
     "dvbs2b200_mixed_fec_decode": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
     "dvbs2b200_mixed_launch_count": (C.c_uint64, [_P]),
+    "dvbs2b200_multi_create": (C.c_int, [C.POINTER(_P), _P, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "dvbs2b200_multi_destroy": (None, [_P]),
+    "dvbs2b200_multi_device_count": (C.c_int, [_P]),
+    "dvbs2b200_multi_code": (_P, [_P, C.c_int]),
+    "dvbs2b200_multi_shard": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "dvbs2b200_multi_fec_decode": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "dvbs2b200_mixed_fec_decode_dev": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, _P, _P, _P]),
+    "dvbs2b200_mixed_create_from_tables": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, _P, _P]),
     "dvbs2b200_estimate_snr": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P]),
     "dvbs2b200_estimate_snr_dev": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, _P]),
     "dvbs2b200_bb_descramble": (C.c_int, [_P, _P, C.c_int, _P]),
@@ -393,14 +401,21 @@ class Code:
 class MixedCodes:
     """A set of MODCODs on one device for mixed (VCM/ACM) batches: frames carry a per-frame code id."""
 
-    def __init__(self, modcods, device=0):
-        """modcods: [(standard, framesize, rate), ...]"""
+    def __init__(self, modcods=None, device=0, tables=None):
+        """modcods: [(standard, framesize, rate), ...], or tables: [packed blob (uint8 array), ...]"""
         self._h = _P()
-        n = len(modcods)
-        std = (C.c_int * n)(*[m[0] for m in modcods])
-        fs = (C.c_int * n)(*[m[1] for m in modcods])
-        rt = (C.c_int * n)(*[m[2] for m in modcods])
-        _check(lib().dvbs2b200_mixed_create(C.byref(self._h), device, n, std, fs, rt))
+        if tables is not None:
+            n = len(tables)
+            bufs = [np.ascontiguousarray(t, dtype=np.uint8) for t in tables]
+            ptrs = (_P * n)(*[b.ctypes.data for b in bufs])
+            sizes = (C.c_size_t * n)(*[b.size for b in bufs])
+            _check(lib().dvbs2b200_mixed_create_from_tables(C.byref(self._h), device, n, ptrs, sizes))
+        else:
+            n = len(modcods)
+            std = (C.c_int * n)(*[m[0] for m in modcods])
+            fs = (C.c_int * n)(*[m[1] for m in modcods])
+            rt = (C.c_int * n)(*[m[2] for m in modcods])
+            _check(lib().dvbs2b200_mixed_create(C.byref(self._h), device, n, std, fs, rt))
         self.infos = []
         for c in range(n):
             info = CodeInfo()
@@ -428,6 +443,16 @@ class MixedCodes:
         k = np.array([i.kbch // 8 for i in self.infos], dtype=np.int64)[code_id]
         return n, k
 
+    def fec_decode_dev(self, code_id, d_llr, max_trials, d_msg, d_trials, d_corr, stream):
+        code_id = _np(code_id, np.uint8)
+        _check(lib().dvbs2b200_mixed_fec_decode_dev(self._h, code_id.size, code_id.ctypes.data, d_llr, max_trials, d_msg, d_trials,
+                                                    d_corr, stream))
+
+    def fec_decode_ptr(self, code_id, llr_ptr, max_trials, msg_ptr, trials_ptr, corr_ptr):
+        code_id = _np(code_id, np.uint8)
+        _check(lib().dvbs2b200_mixed_fec_decode(self._h, code_id.size, code_id.ctypes.data, llr_ptr, max_trials, msg_ptr, trials_ptr,
+                                                corr_ptr))
+
     def fec_decode(self, code_id, llr, max_trials=25):
         """code_id [F] uint8; llr: the frames' int8 LLRs back to back.  Returns (msg bytes back to back,
         trials_left [F], corrections [F])."""
@@ -440,5 +465,42 @@ class MixedCodes:
         trials = np.empty(F, dtype=np.int32)
         corr = np.empty(F, dtype=np.int32)
         _check(lib().dvbs2b200_mixed_fec_decode(self._h, F, code_id.ctypes.data, llr.ctypes.data, max_trials, msg.ctypes.data,
+                                                trials.ctypes.data, corr.ctypes.data))
+        return msg, trials, corr
+
+
+class MultiCode:
+    """One code on several devices of this process (dvbs2b200_multi_*): the batch is cut into contiguous frame ranges."""
+
+    def __init__(self, devices, standard=STANDARD_DVBS2, framesize=FECFRAME_NORMAL, rate=None):
+        self._h = _P()
+        devs = (C.c_int * len(devices))(*devices)
+        _check(lib().dvbs2b200_multi_create(C.byref(self._h), devs, len(devices), standard, framesize, rate))
+        self.info = lookup(standard, framesize, rate)
+        self.N, self.kbch = self.info.n_ldpc, self.info.kbch
+
+    def close(self):
+        if self._h:
+            lib().dvbs2b200_multi_destroy(self._h)
+            self._h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def shard(self, frames, index):
+        a, b = C.c_int(), C.c_int()
+        _check(lib().dvbs2b200_multi_shard(self._h, frames, index, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def fec_decode(self, llr, max_trials=25, term_group=TERM_PER_FRAME):
+        llr = _np(llr, np.int8).reshape(-1, self.N)
+        F = llr.shape[0]
+        msg = np.empty((F, self.kbch // 8), dtype=np.uint8)
+        trials = np.empty(F, dtype=np.int32)
+        corr = np.empty(F, dtype=np.int32)
+        _check(lib().dvbs2b200_multi_fec_decode(self._h, 0, None, None, llr.ctypes.data, F, max_trials, term_group, msg.ctypes.data,
                                                 trials.ctypes.data, corr.ctypes.data))
         return msg, trials, corr

@@ -13,9 +13,14 @@
  *   - a handle is bound to one CUDA device and one code (the reference is CCM: one MODCOD
  *     per block instance) and is used by one host thread at a time (GNU Radio calls
  *     general_work from one thread per block).
- *   - "host" entry points take host pointers (pageable or pinned) and stage through pinned
- *     buffers + the handle's stream; "_dev" entry points take device pointers and a
- *     cudaStream_t (as void*) and are asynchronous on that stream.
+ *   - "host" entry points take host pointers and return when the results are in them.  Pinned /
+ *     registered memory is copied from directly; pageable memory (GNU Radio's buffers) is staged
+ *     through the handle's ring of pinned slots by dvbs2b200_fec_decode (the streaming entry
+ *     point); the other host entry points hand pageable pointers to the driver's own staging.
+ *   - "_dev" entry points take device pointers and a cudaStream_t (as void*) and are
+ *     asynchronous on that stream.  A handle's scratch is shared by all its calls, so the library
+ *     orders them: a call on another stream than the previous one first waits (on the device)
+ *     for the previous call's work.  Symbol buffers must be 16-byte, LLR buffers 4-byte aligned.
  *   - there is NO CPU fallback: without a usable CUDA device every compute entry point
  *     fails with DVBS2B200_ECUDA.
  *
@@ -175,7 +180,35 @@ void dvbs2b200_mixed_destroy(dvbs2b200_mixed* m);
 int dvbs2b200_mixed_code_info(const dvbs2b200_mixed* m, int code, dvbs2b200_code_info* info);
 int dvbs2b200_mixed_fec_decode(dvbs2b200_mixed* m, int frames, const uint8_t* code_id, const int8_t* llr,
                                int max_trials, uint8_t* msg, int32_t* trials_left, int32_t* corrections);
+/* device variant: d_llr / d_msg / status arrays in device memory (code_id stays a host array: it is control
+ * data, read before the call returns); asynchronous on `stream`, which waits for every bucket. */
+int dvbs2b200_mixed_fec_decode_dev(dvbs2b200_mixed* m, int frames, const uint8_t* code_id, const int8_t* d_llr,
+                                   int max_trials, uint8_t* d_msg, int32_t* d_trials_left, int32_t* d_corrections,
+                                   void* stream);
+/* the set from packed tables (dvbs2b200_tables_build on rank 0, ONE broadcast of the concatenated blobs) */
+int dvbs2b200_mixed_create_from_tables(dvbs2b200_mixed** m, int device, int n_codes, const void* const* blobs,
+                                       const size_t* sizes);
 uint64_t dvbs2b200_mixed_launch_count(const dvbs2b200_mixed* m);
+
+/* ---- one code on several devices of ONE process ------------------------------------------------ */
+/* A GNU Radio flowgraph is one process: a block that wants all GPUs of the node cannot use one rank per GPU.
+ * dvbs2b200_multi holds one handle per listed device (the tables are built once on the host and copied to each
+ * device: plain host-to-device copies, no collective is needed inside one process; a device may be listed more
+ * than once).  dvbs2b200_multi_fec_decode is dvbs2b200_fec_decode with the batch cut into contiguous frame
+ * ranges whose boundaries fall on multiples of 32 frames (a reference SIMD batch never straddles devices,
+ * lib/ldpc_decoder/layered_decoder.hh:153); the ranges are staged and decoded concurrently (one library-owned
+ * worker per device), the call returns when all are done.  Results are identical to the single-device call.
+ * dvbs2b200_multi_code(m, i) exposes handle i for the other entry points (demap, bch, ...). */
+typedef struct dvbs2b200_multi dvbs2b200_multi;
+int dvbs2b200_multi_create(dvbs2b200_multi** m, const int* devices, int n_devices, int standard, int framesize,
+                           int rate);
+void dvbs2b200_multi_destroy(dvbs2b200_multi* m);
+int dvbs2b200_multi_device_count(const dvbs2b200_multi* m);
+dvbs2b200_code* dvbs2b200_multi_code(dvbs2b200_multi* m, int index);
+int dvbs2b200_multi_shard(const dvbs2b200_multi* m, int frames, int index, int* first, int* count);
+int dvbs2b200_multi_fec_decode(dvbs2b200_multi* m, int constellation, const float* iq, const float* n0,
+                               const int8_t* llr, int frames, int max_trials, int term_group, uint8_t* msg,
+                               int32_t* trials_left, int32_t* corrections);
 
 /* ---- SNR estimate of the demapper block ------------------------------------------------------- */
 /* dvbs2b200_estimate_snr <- the initial estimate in general_work  lib/xfecframe_demapper_cb_impl.cc:123-146
