@@ -119,7 +119,6 @@ struct dvbs2b200_code {
     uint8_t* d_blob = nullptr;
     size_t ldpc_smem = 0;
     int ldpc_ctas = 0;      // resident LDPC CTAs per SM
-    int ldpc_ctas_tmem = 0; // same for the kernel variant that keeps wavefront state in tensor memory
     uint64_t launches = 0;
     // staging for the host-pointer entry points
     DevBuf d_in, d_mid, d_out, d_post, d_i32a, d_i32b, d_n0, d_llr, d_sync, d_scratch, d_flag, d_prof;
@@ -216,22 +215,15 @@ int create_from_blob(dvbs2b200_code** out, int device, std::vector<uint8_t>&& bl
         (e = mixed_preload()) != cudaSuccess)
         return bail(cuda_fail(e, "kernel preload"));
     h->ldpc_smem = ldpc_smem_bytes(h->hdr.N, h->hdr.smem_bytes, h->hdr.chain_scratch != 0, nullptr);
-    auto ctas_per_sm = h->hdr.split_steps ? ldpc_ctas_per_sm_split : ldpc_ctas_per_sm_wavefront;
     if (h->hdr.max_cnt <= 28 && h->ldpc_smem <= (size_t)h->smem_optin)
-        h->ldpc_ctas = ctas_per_sm(h->hdr.max_cnt, h->hdr.uniform_cnt != 0, false, h->ldpc_smem);
-    if (h->ldpc_ctas > 0 && h->hdr.tmem_cols > 0 && !h->hdr.split_steps)
-        h->ldpc_ctas_tmem = ctas_per_sm(h->hdr.max_cnt, h->hdr.uniform_cnt != 0, true, h->ldpc_smem);
-    if (h->hdr.split_steps && h->hdr.level_calls && h->hdr.max_cnt <= 13) // the split build's other kernel variant
-        h->ldpc_ctas = ctas_per_sm(h->hdr.max_cnt, h->hdr.uniform_cnt != 0, true, h->ldpc_smem);
+        h->ldpc_ctas = ldpc_ctas_per_sm(h->hdr.max_cnt, h->hdr.uniform_cnt != 0, h->ldpc_smem);
     if (getenv("DVBS2B200_DEBUG"))
-        fprintf(stderr, "[dvbs2b200] table %d: %s steps, ldpc smem %zu B, %d CTAs/SM (%d with TMEM state, %d columns)\n", h->hdr.table,
-                h->hdr.split_steps ? "split" : "wavefront", h->ldpc_smem, h->ldpc_ctas, h->ldpc_ctas_tmem, h->hdr.tmem_cols);
+        fprintf(stderr, "[dvbs2b200] table %d: ldpc smem %zu B, %d CTAs/SM, %d state words per check-node pair\n", h->hdr.table,
+                h->ldpc_smem, h->ldpc_ctas, h->hdr.msg_words);
     if (const char* cap = getenv("DVBS2B200_LDPC_CTAS_PER_SM")) { // tuning knob: cap the resident CTAs per SM
         int c = atoi(cap);
         if (c > 0 && c < h->ldpc_ctas)
             h->ldpc_ctas = c;
-        if (c > 0 && c < h->ldpc_ctas_tmem)
-            h->ldpc_ctas_tmem = c;
     }
     *out = h;
     return DVBS2B200_OK;
@@ -280,9 +272,9 @@ struct StreamOrder {
 int ldpc_out_bytes(const BlobHeader& h, int output_mode) { return (output_mode ? h.kldpc_out : h.N) / 8; }
 
 // grid size: persistent CTAs, as many as are resident at once; in group mode a multiple of the group
-int ldpc_grid(const dvbs2b200_code* h, int frames, int group, bool tmem)
+int ldpc_grid(const dvbs2b200_code* h, int frames, int group)
 {
-    const int resident = h->sm_count * ((tmem && !h->hdr.split_steps) ? h->ldpc_ctas_tmem : h->ldpc_ctas);
+    const int resident = h->sm_count * h->ldpc_ctas;
     int grid = std::min(frames, resident);
     if (group > 1)
         grid = std::min(frames, (resident / group) * group);
@@ -327,14 +319,9 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
     p.work = reinterpret_cast<const uint16_t*>(h->d_blob + hd.order_off);
     size_t smem = ldpc_smem_bytes(hd.N, hd.smem_bytes, hd.chain_scratch != 0, &p);
     const int group = term_group > 1 ? term_group : 0;
-    // wavefront state in tensor memory: per-frame mode only (the cooperative launch of the group mode is
-    // sized by the occupancy calculator, which does not co-schedule kernels that use TMEM)
-    // fourth kernel-variant flag: tensor-memory state (wavefront build) / out-of-line level calls (split build)
-    const bool tmem = hd.split_steps ? (hd.level_calls != 0 && hd.max_cnt <= 13)
-                                     : (group == 0 && h->ldpc_ctas_tmem >= h->ldpc_ctas && h->ldpc_ctas_tmem > 0 && !getenv("DVBS2B200_NO_TMEM"));
-    const int grid = ldpc_grid(h, frames, group, tmem);
+    const int grid = ldpc_grid(h, frames, group);
     {
-        int rc = h->d_scratch.ensure((size_t)grid * hd.R * hd.msg_words * sizeof(uint32_t));
+        int rc = h->d_scratch.ensure((size_t)grid * (hd.R / 2) * hd.msg_words * sizeof(uint32_t));
         if (rc)
             return rc;
         p.msg_scratch = (uint32_t*)h->d_scratch.p;
@@ -351,9 +338,11 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
     p.llr_post = d_llr_post;
     p.trials_left = d_trials_left;
     p.sm_count = h->sm_count;
-    p.stagger_ns = 0;
-    if (const char* sg = getenv("DVBS2B200_STAGGER_NS"))
-        p.stagger_ns = (unsigned int)atoi(sg);
+    p.two = 2u;
+    p.four = 4u;
+    p.c30 = 1u << 30;
+    p.c16 = 1u << 16;
+    p.neg1 = 0xffffffffu;
     if (p.group) {
         size_t words = (size_t)(frames / p.group) * (max_trials + 2);
         int rc = h->d_sync.ensure(words * sizeof(unsigned));
@@ -374,7 +363,7 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
         p.prof = (unsigned long long*)h->d_prof.p;
         CU(cudaMemsetAsync(p.prof, 0, (size_t)grid * 16 * sizeof(unsigned long long), stream));
     }
-    cudaError_t e = (hd.split_steps ? ldpc_launch_split : ldpc_launch_wavefront)(p, hd.max_cnt, hd.uniform_cnt != 0, tmem, grid, smem, stream);
+    cudaError_t e = ldpc_launch(p, hd.max_cnt, hd.uniform_cnt != 0, grid, smem, stream);
     if (e != cudaSuccess)
         return cuda_fail(e, "ldpc_launch");
     if (prof_path) {
@@ -382,13 +371,9 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
         CU(cudaStreamSynchronize(stream));
         CU(cudaMemcpy(host.data(), h->d_prof.p, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         if (FILE* f = fopen(prof_path, "w")) {
-            static const char* names[13] = { "load", "syndrome_pass", "pair_steps", "narrow_runs", "wide_steps", "iteration_end",
-                                             "output", "total",
-                                             // split steps.  level form: barrier wait, node work, hand-over, warp-levels, prologue;
-                                             // chain form: records + barrier, warp 0's walk, wait for the other walkers, levels, -
-                                             "split_wait_or_records", "split_node_work", "split_handover_or_wait", "split_levels",
-                                             "split_prologue" };
-            for (int k = 0; k < 13; ++k) {
+            static const char* names[11] = { "load", "syndrome_pass", "pair_steps", "split_phase1", "split_serial_phase", "split_phase3",
+                                             "iteration_end", "output", "total", "n_pair_steps", "n_split_steps" };
+            for (int k = 0; k < 11; ++k) {
                 double sum = 0;
                 for (int b = 0; b < grid; ++b)
                     sum += (double)host[(size_t)b * 16 + k];

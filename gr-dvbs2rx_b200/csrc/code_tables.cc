@@ -37,45 +37,7 @@ const ModcodDef* find_modcod(int standard, int framesize, int rate)
 // such layers we compute level[j] = 1 + max(level[j'] : j' < j touches one of j's bits); check
 // nodes of equal level are independent, and running the levels in order reproduces the serial
 // result bit for bit.
-// Which form of the conflict layers is faster was measured per code on B200 (profiles/r01b_sweep_configs.jsonl):
-// with the call-free split kernel the split steps win on all five BASELINE codes (1/2 normal 82 k -> 97 k,
-// 3/4 normal 77 k -> 133 k, 3/5 normal 70 k -> 91 k, 2/3 short 100 k -> 155 k, 9/10 normal 70 k -> 80 k frames/s),
-// so they are the default; the wavefront build stays in the library for A/B runs (DVBS2B200_SPLIT=0).
-bool choose_split(const LdpcTableDef& def)
-{
-    (void)def;
-    if (const char* env = getenv("DVBS2B200_SPLIT"))
-        return atoi(env) != 0;
-    return true;
-}
-
-// Split build, which kernel variant: with or without the out-of-line level-form copies (ldpc_kernel.cu).
-// Measured on B200: the call-free variant wins wherever most conflict layers take the chain form (1/2 normal
-// 84 k -> 97 k, 3/4 normal 118 k -> 132 k frames/s: no local-memory frame, DRAM traffic back to the compulsory
-// bytes); short frames with a good share of three/four-link level-form layers keep the calls (2/3 short:
-// 119 k without, 154 k with).  DVBS2B200_LEVEL_CALLS=0/1 overrides.
-bool choose_level_calls(const LdpcTableDef& def)
-{
-    if (const char* env = getenv("DVBS2B200_LEVEL_CALLS"))
-        return atoi(env) != 0;
-    std::vector<std::vector<int>> groups(def.q);
-    for (int c = 0; c < def.n_circ; ++c)
-        groups[def.circ[c] >> 17].push_back((int)((def.circ[c] >> 9) & 0xff));
-    int conflict = 0, level_form = 0, max_cnt = 0;
-    for (auto& g : groups) {
-        std::sort(g.begin(), g.end());
-        max_cnt = std::max(max_cnt, (int)g.size());
-        int shared = 0;
-        for (size_t a = 0; a < g.size(); ++a)
-            if ((a && g[a] == g[a - 1]) || (a + 1 < g.size() && g[a] == g[a + 1]))
-                ++shared;
-        conflict += shared > 0;
-        level_form += shared > 2;
-    }
-    return def.N <= 16200 && max_cnt <= 13 && 4 * level_form >= conflict && level_form > 0;
-}
-
-void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem, int split_arg)
+void build_schedule(const LdpcTableDef& def, Schedule& s)
 {
     const int q = def.q;
     s = Schedule();
@@ -87,8 +49,6 @@ void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem, int spl
     }
     const int ngroups = def.K / 360;
     std::vector<int> last(ngroups * 360);
-    const bool split = split_arg < 0 ? choose_split(def) : split_arg != 0;
-    s.split = split;
     const char* env_chain = getenv("DVBS2B200_CHAIN"); // diagnostics: 0 = level-by-level form for every split step
     const bool chain = !(env_chain && atoi(env_chain) == 0);
     for (int i = 0; i < q; ++i) {
@@ -139,7 +99,7 @@ void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem, int spl
         }
         s.steps_per_iter += depth;
         s.max_depth = std::max(s.max_depth, depth);
-        if (split) { // n_shared <= kMaxSharedLinks holds for all 57 tables (asserted by tests/test_host_cpu.py)
+        { // n_shared <= kMaxSharedLinks holds for all 57 tables (asserted by tests/test_host_cpu.py)
             // One "split" step: private links of all 360 check nodes in parallel, the shared links level by
             // level (code_tables.h).  work[] holds level[j] for j = 0..359.
             StepRec st;
@@ -175,145 +135,36 @@ void build_schedule(const LdpcTableDef& def, Schedule& s, bool use_tmem, int spl
             s.steps.push_back(st);
             continue;
         }
-        for (int lv = 1; lv <= depth; ++lv) {
-            StepRec st;
-            st.layer = (uint8_t)i;
-            st.run_len = 0;
-            st.work_off = (uint32_t)s.order.size();
-            for (int j = 0; j < 360; ++j)
-                if (level[j] == lv)
-                    s.order.push_back((uint16_t)j);
-            st.count = (uint16_t)(s.order.size() - st.work_off);
-            s.steps.push_back(st);
-        }
     }
 
     // ---- barrier placement ---------------------------------------------------------------------
-    // dirty_all / dirty_sub: groups written since the last block barrier by steps every warp runs /
-    // by link-parallel runs (a subset of the warps).  Group index ngroups stands for "parity bits touched across threads".
-    std::vector<char> dirty_all(ngroups + 1, 0), dirty_sub(ngroups + 1, 0);
-    auto clear = [&]() {
-        std::fill(dirty_all.begin(), dirty_all.end(), 0);
-        std::fill(dirty_sub.begin(), dirty_sub.end(), 0);
-    };
-    auto group_lanes = [&](int layer) { // lanes per check node in the link-parallel path
-        const int deg = (int)per_layer[layer].size() + 2;
-        return deg <= 8 ? 8 : deg <= 16 ? 16 : 32;
-    };
-    // class of a wavefront step: 0 wide (all warps), 1 narrow scalar on warp 0, 2 link parallel.
-    // Instruction cost model (measured on B200): a scalar check-node update is ~55 warp instructions
-    // per link for up to 32 nodes, a link-parallel pass ~150 per warp of (node, link) lanes.
-    // tuning knobs (diagnostics): DVBS2B200_LP_LANES = link-parallel up to that many (node, link) lanes
-    // per level instead of the cost model; DVBS2B200_W0_MAX = largest level run on warp 0 alone
-    const char* env_lp = getenv("DVBS2B200_LP_LANES");
-    const char* env_w0 = getenv("DVBS2B200_W0_MAX");
-    const int lp_lanes = env_lp ? atoi(env_lp) : -1;
-    const int w0_max = env_w0 ? atoi(env_w0) : 32;
-    auto step_class = [&](const StepRec& st) {
-        if (st.count == 0 || (st.work_off & kStepSplit))
-            return 0;
-        const int G = group_lanes(st.layer), deg = (int)per_layer[st.layer].size() + 2;
-        const int lp_warps = ((int)st.count * G + 31) / 32;
-        if (lp_lanes >= 0) {
-            if ((int)st.count * G <= lp_lanes)
-                return 2;
-        } else if (st.count <= 32) {
-            if (lp_warps <= 6 && 150 * lp_warps < 55 * deg)
-                return 2;
-            // high-degree codes (> 16 links): a scalar level is a ~1600-instruction dependent chain on one
-            // warp; spreading it over the links pays up to 14 nodes per level even with several passes
-            if (G == 32 && st.count <= 14)
-                return 2;
-        }
-        return (int)st.count <= w0_max ? 1 : 0;
-    };
-    // runs of consecutive narrow steps of one layer and one class
-    for (size_t k = 0; k < s.steps.size();) {
-        const int cls = step_class(s.steps[k]);
-        if (cls == 0) {
-            ++k;
-            continue;
-        }
-        size_t e = k;
-        int lanes = 0;
-        while (e < s.steps.size() && e - k < 255 && s.steps[e].layer == s.steps[k].layer && step_class(s.steps[e]) == cls) {
-            lanes = std::max(lanes, (int)s.steps[e].count * group_lanes(s.steps[e].layer));
-            ++e;
-        }
-        const int warps = cls == 2 ? std::min(6, (lanes + 31) / 32) : 1;
-        s.steps[k].run_len = (uint8_t)(e - k);
-        for (size_t t = k; t < e; ++t)
-            s.steps[t].work_off |= kStepRun | ((uint32_t)warps << kStepWarpsShift) | (cls == 2 ? kStepLinkParallel : 0u);
-        k = e;
-    }
+    // dirty: groups written since the last block barrier.  Parity links are thread private in every step (pair
+    // and split steps keep the pair mapping), except between the last layer and layer 0 of the next iteration,
+    // which starts behind a barrier anyway.
+    std::vector<char> dirty(ngroups, 0);
+    bool parity_dirty = false; // layer 0 wrote the parity bits q*(p-1) + q-1 that thread p-1 owns in layer q-1
     for (size_t k = 0; k < s.steps.size(); ++k) {
         StepRec& st = s.steps[k];
         const bool is_split = (st.work_off & kStepSplit) != 0;
-        // a split step keeps the pair mapping (thread p owns check nodes p and p+180): parity links stay private
-        const bool conflict_layer = st.count != 0 && !is_split;
-        const bool sub = (st.work_off & kStepRun) != 0; // runs on a subset of the warps
-        const bool inside_run = sub && st.run_len == 0;          // ordered by the run's own barrier
-        std::vector<int> groups;
-        for (auto& ga : per_layer[st.layer])
-            groups.push_back(ga.first);
-        // conflict layers run single check nodes on arbitrary threads: their parity links are not
-        // thread private, and the neighbouring layers' parity links collide with them
-        const bool prev_conflict = k > 0 && s.steps[k - 1].count != 0 && !(s.steps[k - 1].work_off & kStepSplit);
         bool need = false;
-        for (int g : groups)
-            need |= dirty_all[g] || (!inside_run && dirty_sub[g]);
-        if (conflict_layer || prev_conflict) // cross-thread parity access: every earlier step wrote parity
-            need |= dirty_all[ngroups] || (!inside_run && dirty_sub[ngroups]);
-        groups.push_back(ngroups); // every step writes parity bits
+        for (auto& ga : per_layer[st.layer])
+            need |= dirty[ga.first] != 0;
+        if (st.layer == q - 1 && parity_dirty)
+            need = true;
         if (k == 0)
             need = false; // the iteration starts behind a barrier
-        if (inside_run)
-            need = false; // (dirty_all was cleared by the barrier in front of the run)
-        if (need) {
+        // a split step always starts behind a block barrier: its scratch and named barriers are reused from
+        // one split step to the next, and its serial phase reads what any thread wrote before
+        if (need || (is_split && k > 0)) {
             st.work_off |= kStepBarrierBefore;
             s.barriers_per_iter++;
-            clear();
+            std::fill(dirty.begin(), dirty.end(), 0);
+            parity_dirty = false;
         }
-        if (is_split && !need) {
-            // the named barriers of the levels are reused from one split step to the next: keep a block
-            // barrier between them and whatever ran before
-            st.work_off |= kStepBarrierBefore;
-            s.barriers_per_iter++;
-            clear();
-        }
-        for (int g : groups)
-            (sub ? dirty_sub : dirty_all)[g] = 1;
-    }
-
-    // ---- tensor-memory columns for the state of wavefront steps (code_tables.h) --------------------
-    s.tcol.assign(s.steps.size(), kNoTmem);
-    if (use_tmem && s.max_cnt <= 13) { // one-word state only
-        int next_col = 0;
-        auto cols_needed = [&](const StepRec& st) {
-            if (st.count == 0 || (st.work_off & (kStepLinkParallel | kStepSplit)))
-                return 0;
-            if (st.work_off & kStepRun)
-                return 1;                          // warp 0, one pass
-            return 2 * (((int)st.count + 191) / 192); // warps 0-3 and 4-5, per pass
-        };
-        // narrow runs first (they are the deepest chains); a run is placed whole or not at all
-        for (size_t k = 0; k < s.steps.size(); ++k) {
-            const StepRec& st = s.steps[k];
-            if (!(st.work_off & kStepRun) || (st.work_off & kStepLinkParallel) || st.run_len == 0)
-                continue;
-            if (next_col + (int)st.run_len > kTmemCols)
-                continue;
-            for (int t = 0; t < (int)st.run_len; ++t)
-                s.tcol[k + t] = (uint8_t)next_col++;
-        }
-        for (size_t k = 0; k < s.steps.size(); ++k) {
-            const StepRec& st = s.steps[k];
-            const int need = cols_needed(st);
-            if (need == 0 || (st.work_off & kStepRun) || next_col + need > kTmemCols)
-                continue;
-            s.tcol[k] = (uint8_t)next_col;
-            next_col += need;
-        }
+        for (auto& ga : per_layer[st.layer])
+            dirty[ga.first] = 1;
+        if (st.layer == 0)
+            parity_dirty = true;
     }
 }
 
@@ -437,17 +288,18 @@ bool build_blob(int standard, int framesize, int rate, std::vector<uint8_t>& blo
     const uint32_t pp = bch_prim_poly(framesize);
     h.gf_m = poly_m(pp);
     h.kldpc_out = mc->nbch;
-    // compressed check-node state: 6+6 bits of clamped minima, 5 bits argmin, 1 sign bit/link
-    h.msg_words = (s.max_cnt <= 13) ? 1 : 2; // must agree with ldpc_wide_state()
+    // compressed check-node state per check-node pair: one word of clamped minima (4 x 6 bits in bytes) and two
+    // bits (sign, argmin) per link and node, 8 links per word (ldpc_core.cuh)
+    h.msg_words = 1 + (s.max_cnt + 2 + 7) / 8;
     h.n_steps_total = (int32_t)s.steps.size();
     h.n_conflict_layers = s.conflict_layers;
     h.steps_per_iter = s.steps_per_iter;
     h.max_depth = s.max_depth;
     h.uniform_cnt = (s.min_cnt == s.max_cnt) ? 1 : 0;
     h.bch_shorten = ((1u << h.gf_m) - 1) - (uint32_t)mc->nbch;
-    h.split_steps = s.split ? 1u : 0u;
+    h.split_steps = 1u;
     h.chain_scratch = s.has_chain ? 1u : 0u;
-    h.level_calls = (s.split && choose_level_calls(def)) ? 1u : 0u;
+    h.level_calls = 0u;
 
     size_t off = sizeof(BlobHeader);
     h.smem_off = (uint32_t)off;
@@ -457,25 +309,9 @@ bool build_blob(int standard, int framesize, int rate, std::vector<uint8_t>& blo
     off += sizeof(EdgeRec) * s.edges.size();
     h.step_off = (uint32_t)off;
     off += sizeof(StepRec) * s.steps.size();
-    const size_t tcol_off = off;
-    off += s.tcol.size();
     off = align16(off);
     h.smem_bytes = (uint32_t)(off - h.smem_off);
-    // Use the tensor-memory kernel variant only when most of the scalar wavefront steps got columns:
-    // measured on B200, codes where under ~3/4 of them fit (DVB-S2 3/4, 3/5 normal) ran slower with a
-    // partial placement than with all state in L2, codes where they fit (1/2 normal, 2/3 short) faster.
     h.tmem_cols = 0;
-    {
-        int placed = 0, scalar_steps = 0;
-        for (size_t k = 0; k < s.steps.size(); ++k) {
-            if (s.steps[k].count == 0 || (s.steps[k].work_off & (kStepLinkParallel | kStepSplit)))
-                continue;
-            ++scalar_steps;
-            placed += s.tcol[k] != kNoTmem;
-        }
-        if (placed > 0 && 4 * placed >= 3 * scalar_steps)
-            h.tmem_cols = kTmemCols;
-    }
     h.order_off = (uint32_t)off;
     off = align16(off + sizeof(uint16_t) * s.order.size());
     std::vector<uint16_t> al, lg;
@@ -492,7 +328,6 @@ bool build_blob(int standard, int framesize, int rate, std::vector<uint8_t>& blo
     memcpy(blob.data() + h.edge_off, s.edges.data(), sizeof(EdgeRec) * s.edges.size());
     if (!s.steps.empty())
         memcpy(blob.data() + h.step_off, s.steps.data(), sizeof(StepRec) * s.steps.size());
-    memcpy(blob.data() + tcol_off, s.tcol.data(), s.tcol.size());
     if (!s.order.empty())
         memcpy(blob.data() + h.order_off, s.order.data(), sizeof(uint16_t) * s.order.size());
     memcpy(blob.data() + h.antilog_off, al.data(), sizeof(uint16_t) * al.size());
@@ -523,7 +358,7 @@ bool validate_blob(const void* blob, size_t size, std::string& err)
               (size_t)h.smem_off + h.smem_bytes <= size && h.step_off <= h.smem_off + h.smem_bytes && h.order_off <= size &&
               h.n_steps_total > 0 && h.n_steps_total <= h.steps_per_iter &&
               (size_t)h.antilog_off + gfn <= size && (size_t)h.log_off + gfn <= size &&
-              (h.msg_words == 1 || h.msg_words == 2) && h.gf_m >= 14 && h.gf_m <= 16;
+              h.msg_words >= 2 && h.msg_words <= 5 && h.gf_m >= 14 && h.gf_m <= 16;
     if (!ok) {
         err = "table blob failed consistency checks";
         return false;

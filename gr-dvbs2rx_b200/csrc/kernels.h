@@ -13,11 +13,13 @@ struct LdpcLaunch {
     int N, K, R, q, n_circ, n_steps;
     const uint8_t* tab;   // device: [LayerRec q][EdgeRec n_circ][StepRec n_steps], 16-byte aligned
     uint32_t tab_bytes;   // multiple of 16
-    const uint16_t* work; // check-node lists of the conflict steps
+    const uint16_t* work; // level tables of the split steps
     // shared-memory carve-up (bytes from the start of dynamic shared memory)
-    uint32_t smem_tab_off, smem_bar_off, smem_rec_off; // rec: 360 x 8 B node scratch of chain-form split steps (0: none)
-    // per-CTA check-node state, [grid][R * words] uint32, L2 resident
+    uint32_t smem_tab_off, smem_bar_off, smem_rec_off; // rec: 360 x 8 B node records of chain-form split steps (0: none)
+    // per-CTA check-node state, [grid][R/2 pairs x (1 + ceil(deg/8)) words] uint32, L2 resident
     uint32_t* msg_scratch;
+    // two constants the compiler must not see through (they keep shifts / adds on the FMA pipe, ldpc_core.cuh)
+    uint32_t two, four, neg1, c30, c16;
     // batch
     const int8_t* llr; // [frames][N], 4-byte aligned
     // streaming input: *ready counts the chunks of ready_chunk frames that have arrived (null: all there)
@@ -32,26 +34,16 @@ struct LdpcLaunch {
     int out_bytes;
     int8_t* llr_post;     // [frames][N] or null, 4-byte aligned
     int32_t* trials_left; // [frames] or null
-    // optional per-CTA cycle counters [grid][8]: load, syndrome pass, pair steps, runs, wide steps,
-    // iteration-end barrier, output, total (diagnostics: DVBS2B200_PHASE_PROFILE)
+    // optional per-CTA cycle counters [grid][16] (diagnostics build: -DDVBS2_PHASE_PROFILE, DVBS2B200_PHASE_PROFILE)
     unsigned long long* prof;
-    // start-up stagger: the CTAs that share an SM (block index / sm_count apart) start stagger_ns apart, so
-    // that they do not walk the latency-bound conflict layers of the code at the same time
     int sm_count;
-    unsigned int stagger_ns;
 };
 
 // fills the smem_* offsets of p (if non-null) and returns the dynamic shared memory size
 size_t ldpc_smem_bytes(int N, uint32_t tab_bytes, bool chain_scratch, LdpcLaunch* p);
-// Two builds of ldpc_kernel.cu: order-sensitive layers as split steps (_split) or as wavefront steps of whole
-// check nodes (_wavefront, with the tensor-memory state variant `tmem`); the blob says which schedule it holds.
-cudaError_t ldpc_launch_split(const LdpcLaunch& p, int max_cnt, bool uniform, bool tmem, int grid, size_t smem, cudaStream_t stream);
-cudaError_t ldpc_launch_wavefront(const LdpcLaunch& p, int max_cnt, bool uniform, bool tmem, int grid, size_t smem, cudaStream_t stream);
+cudaError_t ldpc_launch(const LdpcLaunch& p, int max_cnt, bool uniform, int grid, size_t smem, cudaStream_t stream);
 // resident CTAs per SM for this code's kernel instantiation (occupancy query)
-int ldpc_ctas_per_sm_split(int max_cnt, bool uniform, bool tmem, size_t smem);
-int ldpc_ctas_per_sm_wavefront(int max_cnt, bool uniform, bool tmem, size_t smem);
-// true when the check-node state takes two words per node (more than 13 data links)
-bool ldpc_wide_state(int max_cnt);
+int ldpc_ctas_per_sm(int max_cnt, bool uniform, size_t smem);
 
 struct BchLaunch {
     const uint8_t* cw; // [frames][n_bytes]
