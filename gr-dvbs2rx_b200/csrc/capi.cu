@@ -214,7 +214,7 @@ int create_from_blob(dvbs2b200_code** out, int device, std::vector<uint8_t>&& bl
     if ((e = bch_preload()) != cudaSuccess || (e = bb_preload()) != cudaSuccess || (e = demap_preload()) != cudaSuccess ||
         (e = mixed_preload()) != cudaSuccess)
         return bail(cuda_fail(e, "kernel preload"));
-    h->ldpc_smem = ldpc_smem_bytes(h->hdr.N, h->hdr.smem_bytes, h->hdr.chain_scratch != 0, nullptr);
+    h->ldpc_smem = ldpc_smem_bytes(h->hdr.N, h->hdr.smem_bytes, h->hdr.chain_scratch, nullptr);
     if (h->hdr.max_cnt <= 28 && h->ldpc_smem <= (size_t)h->smem_optin)
         h->ldpc_ctas = ldpc_ctas_per_sm(h->hdr.max_cnt, h->hdr.uniform_cnt != 0, h->ldpc_smem);
     if (getenv("DVBS2B200_DEBUG"))
@@ -317,7 +317,7 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
     p.tab = h->d_blob + hd.smem_off;
     p.tab_bytes = hd.smem_bytes;
     p.work = reinterpret_cast<const uint16_t*>(h->d_blob + hd.order_off);
-    size_t smem = ldpc_smem_bytes(hd.N, hd.smem_bytes, hd.chain_scratch != 0, &p);
+    size_t smem = ldpc_smem_bytes(hd.N, hd.smem_bytes, hd.chain_scratch, &p);
     const int group = term_group > 1 ? term_group : 0;
     const int grid = ldpc_grid(h, frames, group);
     {
@@ -1480,31 +1480,29 @@ int dvbs2b200_demap_table_dev(dvbs2b200_code* h, int bits, const float* points, 
     for (int k = 0; k < bits; ++k)
         if (row_offsets[k] < 0 || row_offsets[k] + n_syms > hd.N)
             return fail(DVBS2B200_EINVAL, "row offset out of range");
+    if (((uintptr_t)d_iq & 15) || ((uintptr_t)d_llr & 3)) // 128-bit symbol loads, 32-bit packed LLR stores
+        return fail(DVBS2B200_EINVAL, "symbol buffer must be 16-byte aligned and the LLR buffer 4-byte aligned");
+    if (n_syms % 4)
+        return fail(DVBS2B200_EUNSUPPORTED, "symbols per frame must be a multiple of 4");
+    for (int k = 0; k < bits; ++k)
+        if (row_offsets[k] & 3)
+            return fail(DVBS2B200_EINVAL, "row offsets must be multiples of 4");
     DeviceGuard g(h->device);
     StreamOrder so(h, (cudaStream_t)stream);
     cudaStream_t s = (cudaStream_t)stream;
-    int rc = h->d_points.ensure(32 * 2 * sizeof(float) + 8 * sizeof(int));
-    if (rc)
-        return rc;
-    // the table (288 bytes) is sent when it differs from what the device already holds; the copy is ordered on
-    // the caller's stream and its source is a local, hence the synchronisation on a change
-    float hp[64] = { 0 };
-    int hr[8] = { 0 };
-    memcpy(hp, points, sizeof(float) * 2 * ((size_t)1 << bits));
-    memcpy(hr, row_offsets, sizeof(int) * bits);
-    std::vector<uint8_t> want(sizeof(hp) + sizeof(hr));
-    memcpy(want.data(), hp, sizeof(hp));
-    memcpy(want.data() + sizeof(hp), hr, sizeof(hr));
-    if (want != h->points_cache) {
-        CU(cudaStreamSynchronize(s)); // an earlier launch on this stream may still be reading the old table
-        CU(cudaMemcpyAsync(h->d_points.p, want.data(), want.size(), cudaMemcpyHostToDevice, s));
-        CU(cudaStreamSynchronize(s));
-        h->points_cache.swap(want);
+    // the constellation travels in the kernel parameters: nothing to upload, nothing cached on the device
+    TableDemapConst tc;
+    memset(&tc, 0, sizeof(tc));
+    for (int i = 0; i < (1 << bits); ++i) {
+        const float x = points[2 * i], y = points[2 * i + 1];
+        tc.a[i] = -2.0f * x;
+        tc.b[i] = -2.0f * y;
+        tc.c[i] = x * x + y * y;
     }
+    for (int k = 0; k < bits; ++k)
+        tc.row[k] = row_offsets[k];
     TableDemapLaunch p;
     memset(&p, 0, sizeof(p));
-    p.points = (const float*)h->d_points.p;
-    p.row_off = (const int*)((uint8_t*)h->d_points.p + sizeof(hp));
     p.n_syms = n_syms;
     p.bits = bits;
     for (int f0 = 0; f0 < frames; f0 += 32768) {
@@ -1512,7 +1510,7 @@ int dvbs2b200_demap_table_dev(dvbs2b200_code* h, int bits, const float* points, 
         p.iq = d_iq + (size_t)f0 * n_syms * 2;
         p.n0 = d_n0 + f0;
         p.llr = d_llr + (size_t)f0 * hd.N;
-        cudaError_t e = demap_table_launch(p, s);
+        cudaError_t e = demap_table_launch(p, tc, s);
         if (e != cudaSuccess)
             return cuda_fail(e, "demap_table_launch");
         h->launches += 1;

@@ -132,6 +132,8 @@ void build_schedule(const LdpcTableDef& def, Schedule& s)
                     s.has_chain = true;
                 }
             }
+            if (!(st.work_off & kStepChain))
+                s.max_level_shared = std::max(s.max_level_shared, n_shared);
             s.steps.push_back(st);
             continue;
         }
@@ -298,7 +300,7 @@ bool build_blob(int standard, int framesize, int rate, std::vector<uint8_t>& blo
     h.uniform_cnt = (s.min_cnt == s.max_cnt) ? 1 : 0;
     h.bch_shorten = ((1u << h.gf_m) - 1) - (uint32_t)mc->nbch;
     h.split_steps = 1u;
-    h.chain_scratch = s.has_chain ? 1u : 0u;
+    h.chain_scratch = (uint32_t)std::max(s.has_chain ? 360 * 8 : 0, 180 * 4 * s.max_level_shared);
     h.level_calls = 0u;
 
     size_t off = sizeof(BlobHeader);

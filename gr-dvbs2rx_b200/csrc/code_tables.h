@@ -94,7 +94,8 @@ struct BlobHeader {
     uint32_t antilog_off, log_off; // uint16[2^m] each: alpha^i (i < 2^m-1), log(x)
     uint32_t bch_shorten;          // s = 2^m - 1 - nbch
     uint32_t split_steps;          // 1 (conflict layers are split steps)
-    uint32_t chain_scratch;        // 1: some split step is in chain form: the kernel needs the 360 x 8 B node scratch
+    uint32_t chain_scratch;        // bytes of shared-memory scratch the split steps need (chain form: 360 x 8 B node records,
+                                   // level form: 180 x 4 B per shared link)
     uint32_t level_calls;          // unused (0)
 };
 static_assert(sizeof(BlobHeader) % 16 == 0, "header must keep sections 16-byte aligned");
@@ -133,6 +134,7 @@ struct Schedule {
     std::vector<uint16_t> order; // work[]: check-node indices of the conflict steps
     int max_cnt = 0, min_cnt = 1 << 30, steps_per_iter = 0, max_depth = 0, conflict_layers = 0, barriers_per_iter = 0;
     bool has_chain = false; // at least one of them in chain form
+    int max_level_shared = 0; // most shared links in a level-form split step
 };
 void build_schedule(const LdpcTableDef& def, Schedule& s);
 

@@ -156,55 +156,79 @@ __global__ void __launch_bounds__(256) snr_kernel(const SnrLaunch p)
 // (positive = bit 0, the convention of lib/qpsk.h:208-214; for QPSK it reduces to the reference's 2 sqrt(2) x / N0),
 // rounded to nearest even and saturated to int8 like the other two.  Symbol index s = the symbol's bits, first
 // bit = MSB.  Bit k of symbol j goes to llr[row_off[k] + j]: the DVB-S2 block interleaver read back, any column
-// order.  One thread per symbol, the constellation in shared memory; stores coalesce per bit row.
-__global__ void __launch_bounds__(256) demap_table_kernel(const TableDemapLaunch p)
+// order.
+// |y|^2 is common to every distance and cancels in the difference: the metric of point s is |s|^2 - 2 Re(y conj s),
+// two FMAs.  The 2 x BITS minima come from a halving tree: at the level of label bit b the metrics are split by
+// that bit (two minima) and folded pairwise over it for the remaining bits -- 82 min operations instead of 160
+// for 32 points, and the compiler fuses pairs of them into three-input FMNMX3.  A thread demaps four consecutive
+// symbols (two 128-bit loads) and stores one 32-bit word per bit row.
+template <int BITS>
+__global__ void __launch_bounds__(256, 3) demap_table_kernel(const TableDemapLaunch p, const TableDemapConst t)
 {
-    __shared__ float2 s_pts[32];
-    __shared__ int s_row[5];
-    const int frame = blockIdx.y, npts = 1 << p.bits;
-    if (threadIdx.x < npts)
-        s_pts[threadIdx.x] = reinterpret_cast<const float2*>(p.points)[threadIdx.x];
-    if (threadIdx.x < p.bits)
-        s_row[threadIdx.x] = p.row_off[threadIdx.x];
-    __syncthreads();
+    // the constellation rides in the kernel parameters (constant bank): -2 Re s, -2 Im s, |s|^2 are operands of the
+    // FMAs straight from there -- no shared-memory loads, no registers held for them
+    constexpr int NP = 1 << BITS;
+    const int frame = blockIdx.y;
     const float inv_n0 = 1.0f / p.n0[frame];
-    const float2* __restrict__ in = reinterpret_cast<const float2*>(p.iq + (size_t)frame * p.n_syms * 2);
-    int8_t* __restrict__ out = p.llr + (size_t)frame * p.n_syms * p.bits;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p.n_syms; j += gridDim.x * blockDim.x) {
-        const float2 y = __ldcs(in + j);
-        float d0[5], d1[5];
+    const float4* __restrict__ in = reinterpret_cast<const float4*>(p.iq + (size_t)frame * p.n_syms * 2);
+    int8_t* __restrict__ out = p.llr + (size_t)frame * p.n_syms * BITS;
+    const int quads = p.n_syms >> 2; // n_syms is a multiple of 4 for every DVB-S2 frame (checked by the host)
+    for (int qd = blockIdx.x * blockDim.x + threadIdx.x; qd < quads; qd += gridDim.x * blockDim.x) {
+        const float4 y01 = __ldcs(in + 2 * qd), y23 = __ldcs(in + 2 * qd + 1);
+        float yxs[4] = { y01.x, y01.z, y23.x, y23.z }, yys[4] = { y01.y, y01.w, y23.y, y23.w };
+        uint32_t packed[BITS];
 #pragma unroll
-        for (int k = 0; k < 5; ++k)
-            d0[k] = d1[k] = 3.0e38f;
-        for (int s = 0; s < npts; ++s) {
-            const float er = __fsub_rn(y.x, s_pts[s].x), ei = __fsub_rn(y.y, s_pts[s].y);
-            const float d = __fadd_rn(__fmul_rn(er, er), __fmul_rn(ei, ei));
+        for (int k = 0; k < BITS; ++k)
+            packed[k] = 0u;
+#pragma unroll 1 // one symbol at a time: 2^BITS live metrics, not four times that
+        for (int u = 0; u < 4; ++u) {
+            // symbol u of the four (selected without indexing the register arrays dynamically)
+            const float yx = u == 0 ? yxs[0] : u == 1 ? yxs[1] : u == 2 ? yxs[2] : yxs[3];
+            const float yy = u == 0 ? yys[0] : u == 1 ? yys[1] : u == 2 ? yys[2] : yys[3];
+            float v[NP];
 #pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                if (k < p.bits) {
-                    const bool one = (s >> (p.bits - 1 - k)) & 1;
-                    if (one)
-                        d1[k] = fminf(d1[k], d);
-                    else
-                        d0[k] = fminf(d0[k], d);
+            for (int s = 0; s < NP; ++s)
+                v[s] = fmaf(yx, t.a[s], fmaf(yy, t.b[s], t.c[s]));
+            // level b: label bit k = BITS - 1 - lvl is the LOW bit of the current index
+#pragma unroll
+            for (int lvl = 0; lvl < BITS; ++lvl) {
+                const int n = NP >> lvl, k = BITS - 1 - lvl;
+                float d0 = v[0], d1 = v[1];
+#pragma unroll
+                for (int i2 = 2; i2 < n; i2 += 2) {
+                    d0 = fminf(d0, v[i2]);
+                    d1 = fminf(d1, v[i2 + 1]);
                 }
+#pragma unroll
+                for (int i2 = 0; i2 < n; i2 += 2)
+                    v[i2 >> 1] = fminf(v[i2], v[i2 + 1]);
+                const int q8 = convert_8i(__fmul_rn(__fsub_rn(d1, d0), inv_n0));
+                packed[k] |= (uint32_t)(uint8_t)q8 << (8 * u);
             }
         }
 #pragma unroll
-        for (int k = 0; k < 5; ++k)
-            if (k < p.bits)
-                out[s_row[k] + j] = (int8_t)convert_8i(__fmul_rn(__fsub_rn(d1[k], d0[k]), inv_n0));
+        for (int k = 0; k < BITS; ++k)
+            *reinterpret_cast<uint32_t*>(out + t.row[k] + 4 * qd) = packed[k];
     }
 }
 
 } // namespace
 
-cudaError_t demap_table_launch(const TableDemapLaunch& p, cudaStream_t stream)
+cudaError_t demap_table_launch(const TableDemapLaunch& p, const TableDemapConst& t, cudaStream_t stream)
 {
     if (p.frames <= 0)
         return cudaSuccess;
-    dim3 grid((p.n_syms + 255) / 256, p.frames);
-    demap_table_kernel<<<grid, 256, 0, stream>>>(p);
+    if (p.n_syms % 4)
+        return cudaErrorInvalidValue;
+    dim3 grid((p.n_syms / 4 + 255) / 256, p.frames);
+    switch (p.bits) {
+    case 1: demap_table_kernel<1><<<grid, 256, 0, stream>>>(p, t); break;
+    case 2: demap_table_kernel<2><<<grid, 256, 0, stream>>>(p, t); break;
+    case 3: demap_table_kernel<3><<<grid, 256, 0, stream>>>(p, t); break;
+    case 4: demap_table_kernel<4><<<grid, 256, 0, stream>>>(p, t); break;
+    case 5: demap_table_kernel<5><<<grid, 256, 0, stream>>>(p, t); break;
+    default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 
@@ -242,7 +266,7 @@ cudaError_t demap_preload()
 {
     cudaFuncAttributes a;
     cudaError_t e;
-    if ((e = cudaFuncGetAttributes(&a, demap_table_kernel)) != cudaSuccess)
+    if ((e = cudaFuncGetAttributes(&a, demap_table_kernel<4>)) != cudaSuccess || (e = cudaFuncGetAttributes(&a, demap_table_kernel<5>)) != cudaSuccess)
         return e;
     if ((e = cudaFuncGetAttributes(&a, snr_kernel)) != cudaSuccess)
         return e;

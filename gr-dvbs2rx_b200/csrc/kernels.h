@@ -15,7 +15,7 @@ struct LdpcLaunch {
     uint32_t tab_bytes;   // multiple of 16
     const uint16_t* work; // level tables of the split steps
     // shared-memory carve-up (bytes from the start of dynamic shared memory)
-    uint32_t smem_tab_off, smem_bar_off, smem_rec_off; // rec: 360 x 8 B node records of chain-form split steps (0: none)
+    uint32_t smem_tab_off, smem_bar_off, smem_rec_off; // rec: scratch of the split steps
     // per-CTA check-node state, [grid][R/2 pairs x (1 + ceil(deg/8)) words] uint32, L2 resident
     uint32_t* msg_scratch;
     // two constants the compiler must not see through (they keep shifts / adds on the FMA pipe, ldpc_core.cuh)
@@ -40,7 +40,7 @@ struct LdpcLaunch {
 };
 
 // fills the smem_* offsets of p (if non-null) and returns the dynamic shared memory size
-size_t ldpc_smem_bytes(int N, uint32_t tab_bytes, bool chain_scratch, LdpcLaunch* p);
+size_t ldpc_smem_bytes(int N, uint32_t tab_bytes, uint32_t scratch_bytes, LdpcLaunch* p);
 cudaError_t ldpc_launch(const LdpcLaunch& p, int max_cnt, bool uniform, int grid, size_t smem, cudaStream_t stream);
 // resident CTAs per SM for this code's kernel instantiation (occupancy query)
 int ldpc_ctas_per_sm(int max_cnt, bool uniform, size_t smem);
@@ -56,7 +56,7 @@ struct BchLaunch {
     const uint16_t* log;     // [2^m]
     int cw_stride, msg_stride; // bytes between consecutive frames
 };
-constexpr int kBchWarpsPerBlock = 8;
+constexpr int kBchWarpsPerBlock = 32; // persistent CTAs, one per SM
 cudaError_t bch_launch(const BchLaunch& p, cudaStream_t stream);
 
 struct DemapLaunch {
@@ -70,14 +70,17 @@ struct DemapLaunch {
 cudaError_t demap_launch(const DemapLaunch& p, cudaStream_t stream);
 
 struct TableDemapLaunch {
-    const float* iq;     // [frames][n_syms][2]
+    const float* iq;     // [frames][n_syms][2], 16-byte aligned
     const float* n0;     // [frames]
-    int8_t* llr;         // [frames][n_syms * bits]
-    const float* points; // device: [2^bits][2], index = the symbol's bits, first bit = MSB
-    const int* row_off;  // device: [bits], bit k of symbol j -> llr[row_off[k] + j]
+    int8_t* llr;         // [frames][n_syms * bits], 4-byte aligned
     int frames, n_syms, bits;
 };
-cudaError_t demap_table_launch(const TableDemapLaunch& p, cudaStream_t stream);
+// the constellation, by value in the kernel parameters: point s = the symbol's bits, first bit = MSB
+struct TableDemapConst {
+    float a[32], b[32], c[32]; // -2 Re s, -2 Im s, |s|^2
+    int row[5];                // bit k of symbol j -> llr[row[k] + j]
+};
+cudaError_t demap_table_launch(const TableDemapLaunch& p, const TableDemapConst& t, cudaStream_t stream);
 
 struct SnrLaunch {
     const float* iq;   // [frames][n_syms][2]

@@ -142,7 +142,8 @@ struct StateIo {
 // that an earlier level still owns.
 template <int CNT_MAX, int NW>
 __device__ __forceinline__ void level_phase(const FrameCtx& c, const ThreadConst& tc, int layer, bool active, int depth,
-                                            const uint16_t* __restrict__ level_tab, volatile int* progress, SplitRegs<CNT_MAX, NW>& r)
+                                            const uint16_t* __restrict__ level_tab, volatile int* progress, const uint32_t* ops,
+                                            SplitRegs<CNT_MAX, NW>& r)
 {
     int lvA = 0, lvB = 0;
     if (active) {
@@ -172,9 +173,9 @@ __device__ __forceinline__ void level_phase(const FrameCtx& c, const ThreadConst
             asm volatile("bar.sync %0, %1;" ::"r"(1 + lvl % 15), "r"(cnt_cur) : "memory");
         }
         if (active && lvA == lvl)
-            level_node<CNT_MAX, NW>(c, tc, layer, 0, r);
+            level_node<CNT_MAX, NW>(c, tc, layer, 0, ops, r);
         if (active && lvB == lvl) // both nodes of the thread in one level: shallow layers only
-            level_node<CNT_MAX, NW>(c, tc, layer, 1, r);
+            level_node<CNT_MAX, NW>(c, tc, layer, 1, ops, r);
         // hand over to level lvl + 1: if this warp has nodes there it syncs at the top of the loop
         if (lvl < depth && !next_mine)
             asm volatile("bar.arrive %0, %1;" ::"r"(1 + (lvl + 1) % 15), "r"(cnt_next) : "memory");
@@ -232,10 +233,11 @@ __device__ __forceinline__ void chain_walk(uint8_t* __restrict__ L, const ChainR
 #ifndef DVBS2_THREE_CTA_UPTO
 #define DVBS2_THREE_CTA_UPTO 13
 #endif
-// resident CTAs per SM the kernels are compiled for: three wherever the register budget (65536 / 576 = 113) allows
+// resident CTAs per SM the kernels are compiled for: three CTAs are 18 warps = 5 on some scheduler, whose register file
+// holds 16384 registers: 96 per thread at most
 
 template <int CNT_MAX, bool UNIFORM>
-__global__ void __launch_bounds__(kLdpcThreads) __maxnreg__(CNT_MAX <= DVBS2_THREE_CTA_UPTO ? 112 : 168) ldpc_decode_kernel(const LdpcLaunch p)
+__global__ void __launch_bounds__(kLdpcThreads) __maxnreg__(CNT_MAX <= DVBS2_THREE_CTA_UPTO ? 96 : 168) ldpc_decode_kernel(const LdpcLaunch p)
 {
     constexpr int NW = (CNT_MAX + 2 + 7) / 8;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -436,11 +438,13 @@ __global__ void __launch_bounds__(kLdpcThreads) __maxnreg__(CNT_MAX <= DVBS2_THR
                         if (active)
                             chain_p3_links<CNT_MAX, NW>(ctx, tc, out_link1, delta, lin, r);
                     } else {
+                        if (active)
+                            level_prep<CNT_MAX, NW>(ctx, tc, layer, reinterpret_cast<uint32_t*>(rec), r);
                         if (tid == 0)
                             s_progress = 0;
                         __syncthreads();
                         LAP(3);
-                        level_phase<CNT_MAX, NW>(ctx, tc, layer, active, depth, work + work_off, &s_progress, r);
+                        level_phase<CNT_MAX, NW>(ctx, tc, layer, active, depth, work + work_off, &s_progress, reinterpret_cast<const uint32_t*>(rec), r);
                         LAP(4);
                     }
                     if (active) {
@@ -545,7 +549,7 @@ int occupancy_one(size_t smem)
 
 } // namespace
 
-size_t ldpc_smem_bytes(int N, uint32_t tab_bytes, bool chain_scratch, LdpcLaunch* p)
+size_t ldpc_smem_bytes(int N, uint32_t tab_bytes, uint32_t scratch_bytes, LdpcLaunch* p)
 {
     size_t off = ((size_t)N + 15) & ~(size_t)15;
     if (p)
@@ -556,9 +560,8 @@ size_t ldpc_smem_bytes(int N, uint32_t tab_bytes, bool chain_scratch, LdpcLaunch
         p->smem_bar_off = (uint32_t)off;
     off += 16;
     if (p)
-        p->smem_rec_off = chain_scratch ? (uint32_t)off : 0u;
-    if (chain_scratch)
-        off += 360 * sizeof(core::ChainRec); // node records (and, in their first byte, the in-link posteriors the walk saw)
+        p->smem_rec_off = (uint32_t)off;
+    off += scratch_bytes; // split steps: node records of the chain form / shared-link operands of the level form
     return off;
 }
 

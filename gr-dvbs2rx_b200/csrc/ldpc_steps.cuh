@@ -194,28 +194,44 @@ LDPC_HD int half_nonneg(const Acc<NW>& a, int hs)
         n += popc(sgn_word(a, w) & (hs ? 0x55550000u : 0x00005555u));
     return n;
 }
+// Operands of the shared links: addresses and old messages do not depend on what the predecessors do.  One word per
+// (shared link, pair) in the step's shared-memory scratch: byte address of node A's operand (node B's is that ^ 1:
+// the two bytes of one halfword) | -(old message) of node A << 16 | of node B << 24.
 template <int CNT_MAX, int NW>
-LDPC_HD void level_node(const FrameCtx& c, const ThreadConst& tc, int layer, int hs, SplitRegs<CNT_MAX, NW>& r)
+LDPC_HD void level_prep(const FrameCtx& c, const ThreadConst& tc, int layer, uint32_t* ops, SplitRegs<CNT_MAX, NW>& r)
 {
     const LayerRec lr = c.layers[layer];
     const int nshared = (int)lr.conflict, d0 = 2 + r.npriv;
-    const int j = (int)tc.p + kPairs * hs;
+    for (int s = 0; s < nshared; ++s) {
+        const int d = d0 + s;
+        const LinkOp o = data_link(c.edges[lr.edge_begin + r.npriv + s], tc);
+        const uint32_t wsh = pick_word(r.st.W, d >> 3) >> field_shift(d);
+        const uint32_t no = prmt(r.st.candA, r.st.candB, imad(wsh & 0x0303u, 0x11u, 0xc480u));
+        ops[s * kPairs + (int)tc.p] = (o.adr + 1u - o.g2) | ((no & 0xffu) << 16) | ((no >> 16) << 24);
+    }
+}
+// node (pair p, half hs) merges its shared links into its minima / signs and updates those bits
+template <int CNT_MAX, int NW>
+LDPC_HD void level_node(const FrameCtx& c, const ThreadConst& tc, int layer, int hs, const uint32_t* ops, SplitRegs<CNT_MAX, NW>& r)
+{
+    const LayerRec lr = c.layers[layer];
+    const int nshared = (int)lr.conflict, d0 = 2 + r.npriv;
     int k0h = (int)((r.acc.k0 >> (16 * hs)) & 0xffffu), k1h = (int)((r.acc.k1 >> (16 * hs)) & 0xffffu);
     int nn = half_nonneg(r.acc, hs);
     // first pass: v->c values of the shared links as the predecessors left the bits
     for (int s = 0; s < nshared; ++s) {
         const int d = d0 + s;
-        const int a = node_operand_addr(c.edges[lr.edge_begin + r.npriv + s], j);
-        const int xb = clamp255((int)c.L[a] + negold_scalar(r.st, d, hs));
+        const uint32_t w = ops[s * kPairs + (int)tc.p];
+        const uint32_t a = (w & 0xffffu) ^ (uint32_t)hs;
+        const int xb = clamp255((int)c.L[a] + (int)(int8_t)(w >> (16 + 8 * hs)));
         const int key = mag_scalar(xb) * 32 + d;
-        k1h = k1h < (k0h > key ? k0h : key) ? k1h : (k0h > key ? k0h : key);
+        const int hi = k0h > key ? k0h : key;
+        k1h = k1h < hi ? k1h : hi;
         k0h = k0h < key ? k0h : key;
         nn += xb >= 128;
         const uint32_t bit = (xb >= 128 ? 1u : 0u) << (8 + 2 * (d & 3) + 16 * hs);
-        if ((d & 7) < 4)
-            or_word(r.acc.lo, d >> 3, bit);
-        else
-            or_word(r.acc.hi, d >> 3, bit);
+        or_word(r.acc.lo, d >> 3, (d & 7) < 4 ? bit : 0u);
+        or_word(r.acc.hi, d >> 3, (d & 7) < 4 ? 0u : bit);
     }
     const int min0 = k0h >> 5 < 126 ? k0h >> 5 : 126, min1 = k1h >> 5 < 126 ? k1h >> 5 : 126;
     const int arg = k0h & 31;
@@ -223,8 +239,9 @@ LDPC_HD void level_node(const FrameCtx& c, const ThreadConst& tc, int layer, int
     // second pass: the operands are still as read above (each is written once, here)
     for (int s = 0; s < nshared; ++s) {
         const int d = d0 + s;
-        const int a = node_operand_addr(c.edges[lr.edge_begin + r.npriv + s], j);
-        const int xb = clamp255((int)c.L[a] + negold_scalar(r.st, d, hs));
+        const uint32_t w = ops[s * kPairs + (int)tc.p];
+        const uint32_t a = (w & 0xffffu) ^ (uint32_t)hs;
+        const int xb = clamp255((int)c.L[a] + (int)(int8_t)(w >> (16 + 8 * hs)));
         const int m = (d == arg) ? min1 : min0;
         const int neg = pn ^ (xb < 128 ? 1 : 0);
         c.L[a] = (uint8_t)clamp255(xb + (neg ? -m : m));

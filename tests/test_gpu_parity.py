@@ -53,6 +53,31 @@ def test_ldpc_group_termination_matches_reference_semantics(gpu, oracle, group):
     code.close()
 
 
+def test_ldpc_group_termination_more_frames_than_resident_ctas(gpu, oracle):
+    """Group mode with the persistent loop actually looping: 2 x 444 resident CTAs' worth of frames (rounded to whole
+    groups), so every CTA decodes several frames and the per-group arrival counters of different passes interleave.
+    Sampled groups are compared with the oracle's coupled loop (lib/ldpc_decoder/layered_decoder.hh:153)."""
+    d = gpu
+    from dvbs2rx_b200 import vectors
+    group = 32
+    frames = (2 * 444 + group) // group * group  # 896
+    base = 96
+    msg, cw, llr, info = vectors.make_llr_frames(S2, SHORT, d.C1_2, base, 1.55, seed=13)
+    reps = (frames + base - 1) // base
+    # the batch is the 96 distinct frames repeated with a rotation per repetition, so the groups differ in composition
+    llr = np.concatenate([np.roll(llr, 7 * r, axis=0) for r in range(reps)])[:frames]
+    code = d.Code(S2, SHORT, d.C1_2)
+    hard, post, left = code.ldpc_decode(llr, 25, group, d.OM_CODEWORD, want_post=True)
+    assert len(set(left.tolist())) > 1  # the groups really stop at different iterations
+    for g in (0, 5, 13, frames // group - 1):
+        sl = slice(g * group, (g + 1) * group)
+        o_post, o_left = oracle.ldpc_decode(info.table, llr[sl], 25, lanes=group)
+        assert np.array_equal(left[sl], o_left), g
+        assert np.array_equal(post[sl], o_post), g
+        assert np.array_equal(hard[sl], oracle.pack_hard(o_post, info.n_ldpc)), g
+    code.close()
+
+
 def test_ldpc_clean_codeword_returns_max_trials(gpu):
     d = gpu
     from dvbs2rx_b200 import vectors

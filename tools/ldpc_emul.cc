@@ -37,7 +37,7 @@ static int run_frame(const LdpcTableDef& def, const Schedule& s, const int8_t* l
         L[pos_of_bit(n, K, R)] = (uint8_t)(llr[n] ^ 0x80);
     FrameCtx c{ L.data(), s.layers.data(), s.edges.data(), K, q };
     std::vector<RawState<NW>> state((size_t)q * kPairs);
-    std::vector<ChainRec> rec(360);
+    std::vector<ChainRec> rec(360 + 180 * kMaxSharedLinks / 2);
     auto tconst = [](int p) {
         ThreadConst tc;
         tc.p = (uint32_t)p;
@@ -104,11 +104,13 @@ static int run_frame(const LdpcTableDef& def, const Schedule& s, const int8_t* l
                 for (int p = 0; p < kPairs; ++p)
                     chain_p3_links<CNT_MAX, NW>(c, tconst(p), out_link1, delta, reinterpret_cast<const uint8_t*>(rec.data()), regs[p]);
             } else {
+                for (int p = 0; p < kPairs; ++p)
+                    level_prep<CNT_MAX, NW>(c, tconst(p), layer, reinterpret_cast<uint32_t*>(rec.data()), regs[p]);
                 for (int lvl = 1; lvl <= depth; ++lvl)
                     for (int p = 0; p < kPairs; ++p)
                         for (int hs = 0; hs < 2; ++hs)
                             if (level[p + kPairs * hs] == lvl)
-                                level_node<CNT_MAX, NW>(c, tconst(p), layer, hs, regs[p]);
+                                level_node<CNT_MAX, NW>(c, tconst(p), layer, hs, reinterpret_cast<const uint32_t*>(rec.data()), regs[p]);
             }
             // phase 3: every thread finalizes first (reads), then stores -- the kernel has no barrier in between,
             // and needs none: see ldpc_kernel.cu

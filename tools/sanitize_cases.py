@@ -4,10 +4,10 @@
 Cases (each compared with nothing here -- parity is the test suite's job; the sanitizer is the judge):
   pair      QPSK 1/2 normal   pair steps + chain-form split steps, per-frame stop
   level     9/10 normal       level-form split steps (named barriers, progress word), wide state
-  short     2/3 short         level-form through the out-of-line copies (LEVEL_CALLS variant)
+  short     2/3 short         chain and level form on a short frame
   c34       3/4 normal        chain + level mix, two CTAs per SM
   group     1/2 short         group-of-32 termination (cooperative launch, arrival counters), frames = 2 x resident CTAs
-Environment knobs (DVBS2B200_CHAIN=0, DVBS2B200_SPLIT=0, ...) apply as usual.
+Environment knobs (DVBS2B200_CHAIN=0: level form for every split step) apply as usual.
 """
 import os
 import sys
