@@ -1480,13 +1480,13 @@ int dvbs2b200_demap_table_dev(dvbs2b200_code* h, int bits, const float* points, 
     for (int k = 0; k < bits; ++k)
         if (row_offsets[k] < 0 || row_offsets[k] + n_syms > hd.N)
             return fail(DVBS2B200_EINVAL, "row offset out of range");
-    if (((uintptr_t)d_iq & 15) || ((uintptr_t)d_llr & 3)) // 128-bit symbol loads, 32-bit packed LLR stores
-        return fail(DVBS2B200_EINVAL, "symbol buffer must be 16-byte aligned and the LLR buffer 4-byte aligned");
-    if (n_syms % 4)
-        return fail(DVBS2B200_EUNSUPPORTED, "symbols per frame must be a multiple of 4");
+    if (((uintptr_t)d_iq & 15) || ((uintptr_t)d_llr & 1)) // 128-bit symbol loads, 16-bit packed LLR stores
+        return fail(DVBS2B200_EINVAL, "symbol buffer must be 16-byte aligned and the LLR buffer 2-byte aligned");
+    if (n_syms % 2)
+        return fail(DVBS2B200_EUNSUPPORTED, "symbols per frame must be even");
     for (int k = 0; k < bits; ++k)
-        if (row_offsets[k] & 3)
-            return fail(DVBS2B200_EINVAL, "row offsets must be multiples of 4");
+        if (row_offsets[k] & 1)
+            return fail(DVBS2B200_EINVAL, "row offsets must be even");
     DeviceGuard g(h->device);
     StreamOrder so(h, (cudaStream_t)stream);
     cudaStream_t s = (cudaStream_t)stream;
@@ -1889,6 +1889,186 @@ int dvbs2b200_multi_fec_decode(dvbs2b200_multi* m, int constellation, const floa
     for (int i = 0; i < world; ++i)
         if (rcs[i])
             return fail(rcs[i], "device " + std::to_string(m->codes[i]->device) + ": " + errs[i]);
+    return DVBS2B200_OK;
+}
+
+// ---- PL descrambler + pilot-segment de-rotation ---------------------------------------------------------------
+struct dvbs2b200_pl {
+    int device = 0;
+    int gold_code = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf d_rn, d_in, d_out, d_info;
+};
+
+} // extern "C"
+
+namespace {
+constexpr int kPlMaxPayload = 360 * 90 + 22 * 36; // MAX_PLFRAME_PAYLOAD, lib/pl_defs.h:29
+// lib/pl_descrambler.cc:36-98: x and y shift registers of EN 302 307-1 5.5.4, x advanced by the Gold code
+int pl_parity18(long a, long b)
+{
+    a &= b;
+    int c = 0;
+    for (int i = 0; i < 18; ++i)
+        c += (int)((a >> i) & 1);
+    return c & 1;
+}
+void pl_scrambling_codes(int gold_code, std::vector<uint8_t>& rn)
+{
+    rn.assign(kPlMaxPayload + 8, 0);
+    long x = 0x00001, y = 0x3FFFF;
+    for (int n = 0; n < gold_code; ++n) {
+        const int xb = pl_parity18(x, 0x0081);
+        x >>= 1;
+        if (xb)
+            x |= 0x20000;
+    }
+    for (int i = 0; i < kPlMaxPayload; ++i) {
+        const int xa = pl_parity18(x, 0x8050), xb = pl_parity18(x, 0x0081), xc = (int)(x & 1);
+        x >>= 1;
+        if (xb)
+            x |= 0x20000;
+        const int ya = pl_parity18(y, 0x04A1), yb = pl_parity18(y, 0xFF60), yc = (int)(y & 1);
+        y >>= 1;
+        if (ya)
+            y |= 0x20000;
+        rn[i] = (uint8_t)((((xa ^ yb) & 1) << 1) | ((xc ^ yc) & 1));
+    }
+}
+int pl_payload_len(int n_slots, int has_pilots) { return n_slots * 90 + (has_pilots ? ((n_slots - 1) / 16) * 36 : 0); }
+
+int pl_dev(dvbs2b200_pl* h, const float* d_payload, int frames, int n_slots, int has_pilots, const dvbs2b200_pl_frame* d_info,
+           float* d_out, cudaStream_t stream)
+{
+    if (frames < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames");
+    if (n_slots < 1 || n_slots > 360)
+        return fail(DVBS2B200_EINVAL, "n_slots must be 1..360");
+    if (frames == 0)
+        return DVBS2B200_OK;
+    if (!d_payload || !d_info || !d_out)
+        return fail(DVBS2B200_EINVAL, "null buffer");
+    if (((uintptr_t)d_payload & 15) || ((uintptr_t)d_out & 15))
+        return fail(DVBS2B200_EINVAL, "symbol buffers must be 16-byte aligned");
+    static_assert(sizeof(dvbs2b200_pl_frame) == sizeof(PlFrameInfo), "dvbs2b200_pl_frame layout");
+    PlLaunch p;
+    memset(&p, 0, sizeof(p));
+    p.payload = d_payload;
+    p.out = d_out;
+    p.rn = (const uint8_t*)h->d_rn.p;
+    p.info = reinterpret_cast<const PlFrameInfo*>(d_info);
+    p.frames = frames;
+    p.n_slots = n_slots;
+    p.has_pilots = has_pilots ? 1 : 0;
+    p.payload_len = pl_payload_len(n_slots, has_pilots);
+    cudaError_t e = pl_launch(p, stream);
+    if (e != cudaSuccess)
+        return cuda_fail(e, "pl_launch");
+    return DVBS2B200_OK;
+}
+} // namespace
+
+extern "C" {
+
+int dvbs2b200_pl_create(dvbs2b200_pl** out, int device, int gold_code)
+{
+    if (!out || gold_code < 0 || gold_code > 262141)
+        return fail(DVBS2B200_EINVAL, "gold_code must be 0..262141");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(DVBS2B200_ECUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) + "); libdvbs2_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev)
+        return fail(DVBS2B200_EINVAL, "device index out of range");
+    dvbs2b200_pl* h = new (std::nothrow) dvbs2b200_pl();
+    if (!h)
+        return fail(DVBS2B200_ENOMEM, "out of host memory");
+    h->device = device;
+    h->gold_code = gold_code;
+    DeviceGuard g(device);
+    std::vector<uint8_t> rn;
+    pl_scrambling_codes(gold_code, rn);
+    int rc = h->d_rn.ensure(rn.size());
+    if (!rc && (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess)
+        rc = cuda_fail(e, "cudaStreamCreate");
+    if (!rc && (e = cudaMemcpyAsync(h->d_rn.p, rn.data(), rn.size(), cudaMemcpyHostToDevice, h->stream)) != cudaSuccess)
+        rc = cuda_fail(e, "cudaMemcpy(scrambling codes)");
+    if (!rc && (e = cudaStreamSynchronize(h->stream)) != cudaSuccess)
+        rc = cuda_fail(e, "cudaStreamSynchronize");
+    if (!rc && (e = pl_preload()) != cudaSuccess)
+        rc = cuda_fail(e, "kernel preload");
+    if (rc) {
+        dvbs2b200_pl_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return DVBS2B200_OK;
+}
+
+void dvbs2b200_pl_destroy(dvbs2b200_pl* h)
+{
+    if (!h)
+        return;
+    DeviceGuard g(h->device);
+    if (h->stream) {
+        cudaStreamSynchronize(h->stream);
+        cudaStreamDestroy(h->stream);
+    }
+    for (DevBuf* b : { &h->d_rn, &h->d_in, &h->d_out, &h->d_info })
+        b->release();
+    delete h;
+}
+
+int dvbs2b200_pl_scrambling_codes(int gold_code, uint8_t* rn, int n)
+{
+    if (!rn || n < 0 || n > kPlMaxPayload || gold_code < 0 || gold_code > 262141)
+        return fail(DVBS2B200_EINVAL, "bad argument");
+    std::vector<uint8_t> all;
+    pl_scrambling_codes(gold_code, all);
+    memcpy(rn, all.data(), (size_t)n);
+    return DVBS2B200_OK;
+}
+
+int dvbs2b200_pl_payload_len(int n_slots, int has_pilots) { return pl_payload_len(n_slots, has_pilots); }
+
+int dvbs2b200_pl_descramble_derotate_dev(dvbs2b200_pl* h, const float* d_payload, int frames, int n_slots, int has_pilots,
+                                         const dvbs2b200_pl_frame* d_info, float* d_xfecframe, void* stream)
+{
+    if (!h)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    DeviceGuard g(h->device);
+    return pl_dev(h, d_payload, frames, n_slots, has_pilots, d_info, d_xfecframe, (cudaStream_t)stream);
+}
+
+int dvbs2b200_pl_descramble_derotate(dvbs2b200_pl* h, const float* payload, int frames, int n_slots, int has_pilots,
+                                     const dvbs2b200_pl_frame* info, float* xfecframe)
+{
+    if (!h)
+        return fail(DVBS2B200_EINVAL, "null handle");
+    if (frames < 0)
+        return fail(DVBS2B200_EINVAL, "negative frames");
+    if (n_slots < 1 || n_slots > 360)
+        return fail(DVBS2B200_EINVAL, "n_slots must be 1..360");
+    if (frames == 0)
+        return DVBS2B200_OK;
+    if (!payload || !info || !xfecframe)
+        return fail(DVBS2B200_EINVAL, "null buffer");
+    DeviceGuard g(h->device);
+    const size_t in_bytes = (size_t)frames * pl_payload_len(n_slots, has_pilots) * 8, out_bytes = (size_t)frames * n_slots * 90 * 8;
+    int rc;
+    if ((rc = h->d_in.ensure(in_bytes)) || (rc = h->d_out.ensure(out_bytes)) || (rc = h->d_info.ensure((size_t)frames * sizeof(dvbs2b200_pl_frame))))
+        return rc;
+    cudaStream_t s = h->stream;
+    CU(cudaMemcpyAsync(h->d_in.p, payload, in_bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->d_info.p, info, (size_t)frames * sizeof(dvbs2b200_pl_frame), cudaMemcpyHostToDevice, s));
+    rc = pl_dev(h, (const float*)h->d_in.p, frames, n_slots, has_pilots, (const dvbs2b200_pl_frame*)h->d_info.p, (float*)h->d_out.p, s);
+    if (rc) {
+        cudaStreamSynchronize(s);
+        return rc;
+    }
+    CU(cudaMemcpyAsync(xfecframe, h->d_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
     return DVBS2B200_OK;
 }
 

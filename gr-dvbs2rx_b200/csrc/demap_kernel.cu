@@ -172,24 +172,23 @@ __global__ void __launch_bounds__(256, 3) demap_table_kernel(const TableDemapLau
     const float inv_n0 = 1.0f / p.n0[frame];
     const float4* __restrict__ in = reinterpret_cast<const float4*>(p.iq + (size_t)frame * p.n_syms * 2);
     int8_t* __restrict__ out = p.llr + (size_t)frame * p.n_syms * BITS;
-    const int quads = p.n_syms >> 2; // n_syms is a multiple of 4 for every DVB-S2 frame (checked by the host)
-    for (int qd = blockIdx.x * blockDim.x + threadIdx.x; qd < quads; qd += gridDim.x * blockDim.x) {
-        const float4 y01 = __ldcs(in + 2 * qd), y23 = __ldcs(in + 2 * qd + 1);
-        float yxs[4] = { y01.x, y01.z, y23.x, y23.z }, yys[4] = { y01.y, y01.w, y23.y, y23.w };
+    // two consecutive symbols per thread (one 128-bit load), one 16-bit store per bit row: n_syms and the row offsets are
+    // even for every DVB-S2 APSK frame (4050, 16200, 3240, 12960 symbols) -- checked by the host
+    const int pairs = p.n_syms >> 1;
+    for (int pr = blockIdx.x * blockDim.x + threadIdx.x; pr < pairs; pr += gridDim.x * blockDim.x) {
+        const float4 y01 = __ldcs(in + pr);
         uint32_t packed[BITS];
 #pragma unroll
         for (int k = 0; k < BITS; ++k)
             packed[k] = 0u;
-#pragma unroll 1 // one symbol at a time: 2^BITS live metrics, not four times that
-        for (int u = 0; u < 4; ++u) {
-            // symbol u of the four (selected without indexing the register arrays dynamically)
-            const float yx = u == 0 ? yxs[0] : u == 1 ? yxs[1] : u == 2 ? yxs[2] : yxs[3];
-            const float yy = u == 0 ? yys[0] : u == 1 ? yys[1] : u == 2 ? yys[2] : yys[3];
+#pragma unroll 1 // one symbol at a time: 2^BITS live metrics
+        for (int u = 0; u < 2; ++u) {
+            const float yx = u == 0 ? y01.x : y01.z, yy = u == 0 ? y01.y : y01.w;
             float v[NP];
 #pragma unroll
             for (int s = 0; s < NP; ++s)
                 v[s] = fmaf(yx, t.a[s], fmaf(yy, t.b[s], t.c[s]));
-            // level b: label bit k = BITS - 1 - lvl is the LOW bit of the current index
+            // level lvl: label bit k = BITS - 1 - lvl is the LOW bit of the current index
 #pragma unroll
             for (int lvl = 0; lvl < BITS; ++lvl) {
                 const int n = NP >> lvl, k = BITS - 1 - lvl;
@@ -208,7 +207,7 @@ __global__ void __launch_bounds__(256, 3) demap_table_kernel(const TableDemapLau
         }
 #pragma unroll
         for (int k = 0; k < BITS; ++k)
-            *reinterpret_cast<uint32_t*>(out + t.row[k] + 4 * qd) = packed[k];
+            *reinterpret_cast<uint16_t*>(out + t.row[k] + 2 * pr) = (uint16_t)packed[k];
     }
 }
 
@@ -218,9 +217,9 @@ cudaError_t demap_table_launch(const TableDemapLaunch& p, const TableDemapConst&
 {
     if (p.frames <= 0)
         return cudaSuccess;
-    if (p.n_syms % 4)
+    if (p.n_syms % 2)
         return cudaErrorInvalidValue;
-    dim3 grid((p.n_syms / 4 + 255) / 256, p.frames);
+    dim3 grid((p.n_syms / 2 + 255) / 256, p.frames);
     switch (p.bits) {
     case 1: demap_table_kernel<1><<<grid, 256, 0, stream>>>(p, t); break;
     case 2: demap_table_kernel<2><<<grid, 256, 0, stream>>>(p, t); break;

@@ -136,6 +136,26 @@ cudaError_t scatter_launch(const uint8_t* src, const unsigned long long* off, ui
                            const int32_t* v1, const int32_t* pos, int32_t* o0, int32_t* o1, cudaStream_t stream);
 
 
+// ---- PL descrambler + pilot-segment de-rotation (pl_kernel.cu) ----------------------------------------------
+// per PLFRAME: what the frame synchroniser estimated (lib/plsync_cc_impl.cc: plframe_info_t, freq_sync pilot phases);
+// the layout is dvbs2b200_pl_frame of include/dvbs2_b200.h
+struct PlFrameInfo {
+    float plheader_phase;
+    float fine_foffset;   // normalised (cycles per symbol); used only when coarse_corrected
+    int coarse_corrected;
+    int reserved;
+    float pilot_phase[22];
+};
+struct PlLaunch {
+    const float* payload;    // [frames][payload_len][2], 16-byte aligned rows (payload_len even)
+    float* out;              // [frames][n_slots * 90][2]
+    const uint8_t* rn;       // [>= payload_len] scrambling codes 0..3
+    const PlFrameInfo* info; // [frames] (device)
+    int frames, n_slots, has_pilots, payload_len;
+};
+cudaError_t pl_launch(const PlLaunch& p, cudaStream_t stream);
+cudaError_t pl_preload();
+
 // load the kernels of a translation unit ahead of their first launch (see bch_kernel.cu)
 cudaError_t bch_preload();
 cudaError_t bb_preload();

@@ -88,6 +88,12 @@ _SIGS = {
     "dvbs2b200_multi_code": (_P, [_P, C.c_int]),
     "dvbs2b200_multi_shard": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "dvbs2b200_multi_fec_decode": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "dvbs2b200_pl_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int]),
+    "dvbs2b200_pl_destroy": (None, [_P]),
+    "dvbs2b200_pl_payload_len": (C.c_int, [C.c_int, C.c_int]),
+    "dvbs2b200_pl_scrambling_codes": (C.c_int, [C.c_int, _P, C.c_int]),
+    "dvbs2b200_pl_descramble_derotate": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "dvbs2b200_pl_descramble_derotate_dev": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "dvbs2b200_mixed_fec_decode_dev": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, _P, _P, _P]),
     "dvbs2b200_mixed_create_from_tables": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, _P, _P]),
     "dvbs2b200_estimate_snr": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P]),
@@ -504,3 +510,50 @@ class MultiCode:
         _check(lib().dvbs2b200_multi_fec_decode(self._h, 0, None, None, llr.ctypes.data, F, max_trials, term_group, msg.ctypes.data,
                                                 trials.ctypes.data, corr.ctypes.data))
         return msg, trials, corr
+
+
+PL_FRAME_DTYPE = np.dtype([("plheader_phase", np.float32), ("fine_foffset", np.float32), ("coarse_corrected", np.int32),
+                           ("reserved", np.int32), ("pilot_phase", np.float32, (22,))])
+
+
+def pl_scrambling_codes(gold_code, n):
+    rn = np.zeros(n, dtype=np.uint8)
+    _check(lib().dvbs2b200_pl_scrambling_codes(gold_code, rn.ctypes.data, n))
+    return rn
+
+
+class PlDescrambler:
+    """PL descrambler + pilot-segment de-rotation of one Gold code on one device (dvbs2b200_pl_*)."""
+
+    def __init__(self, gold_code=0, device=0):
+        self._h = _P()
+        _check(lib().dvbs2b200_pl_create(C.byref(self._h), device, gold_code))
+
+    def close(self):
+        if self._h:
+            lib().dvbs2b200_pl_destroy(self._h)
+            self._h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def payload_len(n_slots, has_pilots):
+        return lib().dvbs2b200_pl_payload_len(n_slots, 1 if has_pilots else 0)
+
+    def process(self, payload, n_slots, has_pilots, info):
+        """payload [F, payload_len, 2] float32, info: array of PL_FRAME_DTYPE [F] -> XFECFRAMEs [F, n_slots * 90, 2]."""
+        payload = _np(payload, np.float32).reshape(-1, self.payload_len(n_slots, has_pilots), 2)
+        F = payload.shape[0]
+        info = np.ascontiguousarray(info, dtype=PL_FRAME_DTYPE)
+        assert info.size == F
+        out = np.empty((F, n_slots * 90, 2), dtype=np.float32)
+        _check(lib().dvbs2b200_pl_descramble_derotate(self._h, payload.ctypes.data, F, n_slots, 1 if has_pilots else 0,
+                                                      info.ctypes.data, out.ctypes.data))
+        return out
+
+    def process_dev(self, d_payload, frames, n_slots, has_pilots, d_info, d_out, stream):
+        _check(lib().dvbs2b200_pl_descramble_derotate_dev(self._h, d_payload, frames, n_slots, 1 if has_pilots else 0, d_info, d_out, stream))

@@ -3,9 +3,14 @@
 The reference (gr-dvbs2rx) has no APSK demapper, so nothing here is checked against it.  The tables follow
 EN 302 307-1 clause 5.4.3 (16APSK: 4+12 points, ring ratio gamma = R2/R1 by code rate, table 9) and clause
 5.4.4 (32APSK: 4+12+16 points, gamma1 = R2/R1, gamma2 = R3/R1, table 10), bit labels as in figures 11 and 12,
-energy normalised to 1.  They were written down without access to the standard's text in this build
-environment: verify the label tables against the standard before relying on them for on-air signals.  The
-demapper itself is table driven and independent of them (any labelled constellation of up to 32 points).
+energy normalised to 1.  PARITY UNPINNED: they were written down without access to the standard's text in this
+build environment and no reference implementation exists to check them against.  What IS checked
+(tests/test_apsk_tables.py): ring sizes 4 + 12 (+ 16), equal phase spacing, unit energy, the ring ratios of every code
+rate, Gray labelling along the 4- and 12-point rings (the 16-point ring of 32APSK is quasi-Gray: one or two bits
+between neighbours), one-bit label symmetry under the I / Q mirror images, and the C++ twin of the tables
+(host/dvbs2rx_b200_blocks.cc:apsk_points).  Verify the label tables against the standard before relying on them
+for on-air signals.  The demapper itself is table driven and independent of them (any labelled constellation of up
+to 32 points).
 """
 import numpy as np
 

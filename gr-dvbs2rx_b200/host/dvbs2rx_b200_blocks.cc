@@ -221,7 +221,7 @@ uint64_t bbdeheader_bb::counters(int which)
 
 // ---- xfecframe_demapper_cb ------------------------------------------------------------------------
 xfecframe_demapper_cb::sptr xfecframe_demapper_cb::make(dvb_framesize_t framesize, dvb_code_rate_t rate,
-                                                        dvb_constellation_t constellation)
+                                                        dvb_constellation_t constellation, bool apsk_opt_in)
 {
     sptr b(new xfecframe_demapper_cb());
     b->d_constellation = constellation;
@@ -244,6 +244,14 @@ xfecframe_demapper_cb::sptr xfecframe_demapper_cb::make(dvb_framesize_t framesiz
         } else {
             b->d_rowaddr0 = 0, b->d_rowaddr1 = rows, b->d_rowaddr2 = rows * 2;
         }
+    } else if (apsk_opt_in && (constellation == MOD_16APSK || constellation == MOD_32APSK) &&
+               apsk_points(constellation, rate, b->d_points)) {
+        // not in the reference: bit k of symbol j sits in interleaver column k (EN 302 307-1 5.3.3), rows = N / bits
+        b->d_bits = constellation == MOD_16APSK ? 4 : 5;
+        b->d_table = true;
+        b->d_waiting_first_llr = false; // no estimator for APSK: N0 comes from set_es_n0_db()
+        for (unsigned int k = 0; k < b->d_bits; ++k)
+            b->d_row_offsets.push_back((int)(k * (b->d_fecframe_len / b->d_bits)));
     } else {
         throw std::runtime_error("Unsupported constellation");
     }
@@ -257,6 +265,14 @@ xfecframe_demapper_cb::sptr xfecframe_demapper_cb::make(dvb_framesize_t framesiz
 }
 
 xfecframe_demapper_cb::~xfecframe_demapper_cb() { dvbs2b200_code_destroy(d_code); }
+
+void xfecframe_demapper_cb::set_es_n0_db(float es_n0_db)
+{
+    std::lock_guard<std::mutex> l(d_mutex);
+    d_snr = es_n0_db;
+    d_N0 = std::pow(10.0f, -es_n0_db / 10.0f);
+    d_precision = 4.0f / d_N0;
+}
 
 void xfecframe_demapper_cb::forecast(int noutput_items, gr_vector_int& ninput_items_required)
 {
@@ -298,8 +314,9 @@ int xfecframe_demapper_cb::general_work(int noutput_items, gr_vector_int& /*ninp
         d_frame_cnt++;
     }
     // soft demap + deinterleave of the whole call in one launch, N0 explicit per frame
-    int rc = dvbs2b200_demap(d_code, d_constellation, reinterpret_cast<const float*>(in), n_frames,
-                             d_n0_per_frame.data(), out);
+    int rc = d_table ? dvbs2b200_demap_table(d_code, (int)d_bits, d_points.data(), d_row_offsets.data(), reinterpret_cast<const float*>(in),
+                                             n_frames, d_n0_per_frame.data(), out)
+                     : dvbs2b200_demap(d_code, d_constellation, reinterpret_cast<const float*>(in), n_frames, d_n0_per_frame.data(), out);
     if (rc != DVBS2B200_OK)
         throw std::runtime_error(std::string("dvbs2b200_demap: ") + dvbs2b200_last_error());
     d_consumed = n_frames * d_xfecframe_len;
@@ -309,6 +326,8 @@ int xfecframe_demapper_cb::general_work(int noutput_items, gr_vector_int& /*ninp
 void xfecframe_demapper_cb::handle_llr_pdu(const llr_pdu& pdu)
 {
     std::lock_guard<std::mutex> l(d_mutex);
+    if (d_table)
+        return; // no SNR refinement for the opt-in APSK constellations
     if (!pdu.llr || pdu.n_llr == 0 || pdu.n_llr != (size_t)pdu.simd_size * d_fecframe_len)
         return; // the reference logs and drops malformed PDUs (:193-242)
     size_t n_frames = pdu.n_llr / d_fecframe_len, n_processed = 0;
@@ -350,6 +369,63 @@ void xfecframe_demapper_cb::handle_llr_pdu(const llr_pdu& pdu)
 } // namespace gr
 
 // ---- ldpc_cuda: the decode seam --------------------------------------------------------------------
+// ---- EN 302 307-1 16APSK (clause 5.4.3) / 32APSK (clause 5.4.4) constellations -------------------------------
+// The C++ twin of dvbs2rx_b200/apsk.py (same tables, checked against each other and for the structural invariants
+// in tests/test_apsk_tables.py).  Nothing in the reference can pin them: parity UNPINNED.
+bool apsk_points(gr::dvbs2rx::dvb_constellation_t constellation, gr::dvbs2rx::dvb_code_rate_t rate, std::vector<float>& points)
+{
+    using namespace gr::dvbs2rx;
+    const double pi = 3.14159265358979323846;
+    auto put = [&](double r, double ph) {
+        points.push_back((float)(r * std::cos(ph)));
+        points.push_back((float)(r * std::sin(ph)));
+    };
+    points.clear();
+    if (constellation == MOD_16APSK) {
+        double g;
+        switch (rate) {
+        case C2_3: g = 3.15; break;
+        case C3_4: g = 2.85; break;
+        case C4_5: g = 2.75; break;
+        case C5_6: g = 2.70; break;
+        case C8_9: g = 2.60; break;
+        case C9_10: g = 2.57; break;
+        default: return false;
+        }
+        const double r1 = std::sqrt(4.0 / (1.0 + 3.0 * g * g)), r2 = g * r1;
+        const double outer[12] = { pi / 4, -pi / 4, 3 * pi / 4, -3 * pi / 4, pi / 12, -pi / 12, 11 * pi / 12, -11 * pi / 12,
+                                   5 * pi / 12, -5 * pi / 12, 7 * pi / 12, -7 * pi / 12 };
+        const double inner[4] = { pi / 4, -pi / 4, 3 * pi / 4, -3 * pi / 4 };
+        for (double a : outer)
+            put(r2, a);
+        for (double a : inner)
+            put(r1, a);
+        return true;
+    }
+    if (constellation == MOD_32APSK) {
+        double g1, g2;
+        switch (rate) {
+        case C3_4: g1 = 2.84, g2 = 5.27; break;
+        case C4_5: g1 = 2.72, g2 = 4.87; break;
+        case C5_6: g1 = 2.64, g2 = 4.64; break;
+        case C8_9: g1 = 2.54, g2 = 4.33; break;
+        case C9_10: g1 = 2.53, g2 = 4.30; break;
+        default: return false;
+        }
+        const double r1 = std::sqrt(8.0 / (1.0 + 3.0 * g1 * g1 + 4.0 * g2 * g2)), r2 = g1 * r1, r3 = g2 * r1;
+        const double tab[32][2] = {
+            { r2, pi / 4 }, { r2, 5 * pi / 12 }, { r2, -pi / 4 }, { r2, -5 * pi / 12 }, { r2, 3 * pi / 4 }, { r2, 7 * pi / 12 },
+            { r2, -3 * pi / 4 }, { r2, -7 * pi / 12 }, { r3, pi / 8 }, { r3, 3 * pi / 8 }, { r3, -pi / 4 }, { r3, -pi / 2 },
+            { r3, 3 * pi / 4 }, { r3, pi / 2 }, { r3, -7 * pi / 8 }, { r3, -5 * pi / 8 }, { r2, pi / 12 }, { r1, pi / 4 },
+            { r2, -pi / 12 }, { r1, -pi / 4 }, { r2, 11 * pi / 12 }, { r1, 3 * pi / 4 }, { r2, -11 * pi / 12 }, { r1, -3 * pi / 4 },
+            { r3, 0.0 }, { r3, pi / 4 }, { r3, -pi / 8 }, { r3, -3 * pi / 8 }, { r3, 7 * pi / 8 }, { r3, 5 * pi / 8 }, { r3, pi }, { r3, -3 * pi / 4 } };
+        for (auto& t : tab)
+            put(t[0], t[1]);
+        return true;
+    }
+    return false;
+}
+
 namespace ldpc_cuda {
 namespace {
 dvbs2b200_code* g_code = nullptr; // a process-wide singleton, like the reference's ISA decoders
@@ -549,6 +625,30 @@ void* blk_demap_make(int framesize, int rate, int constellation, char* err, int 
         }
         return nullptr;
     }
+}
+// the opt-in surface: 16APSK / 32APSK through the table-driven demapper, Es/N0 given explicitly
+void* blk_demap_make_apsk(int framesize, int rate, int constellation, float es_n0_db, char* err, int errcap)
+{
+    try {
+        auto* b = new xfecframe_demapper_cb::sptr(xfecframe_demapper_cb::make((dvb_framesize_t)framesize, (dvb_code_rate_t)rate,
+                                                                             (dvb_constellation_t)constellation, /*apsk_opt_in=*/true));
+        (*b)->set_es_n0_db(es_n0_db);
+        return b;
+    } catch (const std::exception& e) {
+        if (err && errcap > 0) {
+            strncpy(err, e.what(), errcap - 1);
+            err[errcap - 1] = 0;
+        }
+        return nullptr;
+    }
+}
+int blk_apsk_points(int constellation, int rate, float* points, int cap)
+{
+    std::vector<float> p;
+    if (!apsk_points((dvb_constellation_t)constellation, (dvb_code_rate_t)rate, p) || (int)p.size() > cap)
+        return -1;
+    memcpy(points, p.data(), p.size() * sizeof(float));
+    return (int)p.size() / 2;
 }
 void blk_demap_free(void* h) { delete (xfecframe_demapper_cb::sptr*)h; }
 int blk_demap_work(void* h, int noutput_items, const float* in, int8_t* out, int* consumed)

@@ -11,6 +11,7 @@
 //   xfecframe_demapper_cb  <- include/gnuradio/dvbs2rx/xfecframe_demapper_cb.h:36-44, lib/xfecframe_demapper_cb_impl.{h,cc}
 //   bbdescrambler_bb       <- include/gnuradio/dvbs2rx/bbdescrambler_bb.h, lib/bbdescrambler_bb_impl.{h,cc}
 //   bbdeheader_bb          <- include/gnuradio/dvbs2rx/bbdeheader_bb.h,    lib/bbdeheader_bb_impl.{h,cc}
+// (apsk_points(): the EN 302 307-1 16APSK / 32APSK constellations, the C++ twin of dvbs2rx_b200/apsk.py)
 // and ldpc_cuda::ldpc_dec_init / ldpc_dec_decode, the pair that slots in beside the reference's ISA
 // namespaces (lib/ldpc_decoder_bb_impl.cc:34-52) behind `int (*decode)(void*, int8_t*, int)`.
 #pragma once
@@ -115,8 +116,12 @@ class xfecframe_demapper_cb
 {
 public:
     typedef std::shared_ptr<xfecframe_demapper_cb> sptr;
-    // throws std::runtime_error("Unsupported constellation") like lib/xfecframe_demapper_cb_impl.cc:70-72
-    static sptr make(dvb_framesize_t framesize, dvb_code_rate_t rate, dvb_constellation_t constellation);
+    // throws std::runtime_error("Unsupported constellation") like lib/xfecframe_demapper_cb_impl.cc:70-72 for anything
+    // but QPSK / 8PSK -- unless apsk_opt_in is set: then MOD_16APSK / MOD_32APSK are demapped by the table-driven
+    // max-log demapper (dvbs2b200_demap_table; EN 302 307-1 constellations of the code rate, tables UNPINNED by any
+    // reference).  The block has no SNR estimator for them: the noise level comes from set_es_n0_db().
+    static sptr make(dvb_framesize_t framesize, dvb_code_rate_t rate, dvb_constellation_t constellation, bool apsk_opt_in = false);
+    void set_es_n0_db(float es_n0_db);
     ~xfecframe_demapper_cb();
     void forecast(int noutput_items, gr_vector_int& ninput_items_required);
     int general_work(int noutput_items, gr_vector_int& ninput_items, gr_vector_const_void_star& input_items,
@@ -144,6 +149,9 @@ private:
     std::array<uint64_t, kPool> d_saved;
     size_t d_idx = 0;
     std::vector<float> d_n0_per_frame, d_snr_per_frame;
+    bool d_table = false;            // APSK (opt-in): table-driven demapper
+    std::vector<float> d_points;     // [2^bits][2]
+    std::vector<int> d_row_offsets;  // [bits]
     std::vector<gr_complex> d_gather_iq;
     std::vector<int8_t> d_gather_llr;
 };
@@ -199,6 +207,10 @@ private:
 
 // The seam of lib/ldpc_decoder_bb_impl.h:41: `code` is [simd][N] int8, overwritten with posterior
 // LLRs; returns trials left (>= 0) or -1; `buffer` (the ISA paths' scratch) is unused.
+// 16APSK / 32APSK points [2^bits][2] of a code rate (index = label, first bit = MSB, unit energy); false if the
+// standard defines no such MODCOD
+bool apsk_points(gr::dvbs2rx::dvb_constellation_t constellation, gr::dvbs2rx::dvb_code_rate_t rate, std::vector<float>& points);
+
 namespace ldpc_cuda {
 int ldpc_dec_init(int standard, int framesize, int rate, int simd_size);
 int ldpc_dec_decode(void* buffer, int8_t* code, int trials);

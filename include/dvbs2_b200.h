@@ -282,6 +282,43 @@ int dvbs2b200_fec_decode_ts_dev(dvbs2b200_code* h, int constellation, const floa
                                 uint8_t* d_ts, size_t ts_cap, int32_t* d_trials_left,
                                 int32_t* d_corrections, void* stream);
 
+/* ---- PL descrambler + pilot-segment de-rotation: PLFRAME payloads -> XFECFRAMEs ------------------------------ */
+/* dvbs2b200_pl_descramble_derotate <- the output stage of plsync_cc_impl::handle_payload  lib/plsync_cc_impl.cc:639-802
+ *                                     (pl_descrambler::descramble                          lib/pl_descrambler.cc:100-104,
+ *                                      the per-16-slot-segment phase correction            lib/plsync_cc_impl.cc:732-776)
+ * dvbs2b200_pl_create              <- pl_descrambler::pl_descrambler / compute_descrambling_sequence
+ *                                                                                           lib/pl_descrambler.cc:15-98
+ * the last data-parallel stage upstream of the demapper.  Frame detection, PLSC decoding and the
+ * phase / frequency ESTIMATES stay where they are (feedback-loop PHY, out of scope); this entry point takes their
+ * results per frame and does the per-symbol work:
+ *   payload    [frames][payload_len][2] float, payload_len = n_slots * 90 + (has_pilots ? ((n_slots - 1) / 16) * 36 : 0):
+ *              the symbols after the PLHEADER, still scrambled, pilot blocks included (dvbs2b200_pl_payload_len)
+ *   info       [frames] dvbs2b200_pl_frame: PLHEADER phase estimate, fine frequency offset (cycles per symbol, applied
+ *              only when coarse_corrected), the phase estimates of the frame's pilot blocks
+ *   xfecframe  [frames][n_slots * 90][2] float: descrambled, pilots removed, de-rotated -- the demapper's input.
+ * The reference de-rotates with VOLK's serial rotator (phase *= increment per sample, float); here each symbol's
+ * phase is evaluated in closed form, so agreement is to float tolerance (about 1e-5 relative), not bit-exact.
+ * Symbol buffers of the _dev variant must be 16-byte aligned. */
+typedef struct dvbs2b200_pl dvbs2b200_pl;
+typedef struct {
+    float plheader_phase;  /* plframe_info_t::plheader_phase */
+    float fine_foffset;    /* plframe_info_t::fine_foffset, normalised */
+    int coarse_corrected;  /* plframe_info_t::coarse_corrected */
+    int reserved;
+    float pilot_phase[22]; /* freq_sync::get_pilot_phase(b), b < n_pilots (MAX_PILOT_BLKS = 22) */
+} dvbs2b200_pl_frame;
+int dvbs2b200_pl_create(dvbs2b200_pl** h, int device, int gold_code);
+void dvbs2b200_pl_destroy(dvbs2b200_pl* h);
+int dvbs2b200_pl_payload_len(int n_slots, int has_pilots);
+/* the scrambling codes R_n (0..3) of the first n payload symbols of a Gold code (host only; descrambling factor
+ * {1, -j, -1, +j}[R_n]) */
+int dvbs2b200_pl_scrambling_codes(int gold_code, uint8_t* rn, int n);
+int dvbs2b200_pl_descramble_derotate(dvbs2b200_pl* h, const float* payload, int frames, int n_slots, int has_pilots,
+                                     const dvbs2b200_pl_frame* info, float* xfecframe);
+int dvbs2b200_pl_descramble_derotate_dev(dvbs2b200_pl* h, const float* d_payload, int frames, int n_slots,
+                                         int has_pilots, const dvbs2b200_pl_frame* d_info, float* d_xfecframe,
+                                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -898,3 +898,85 @@ long orc_bbdeheader_work(orc_bbdeheader* h, const uint8_t* in, int frames, uint8
     }
     return produced;
 }
+
+/* ---- PL descrambler + pilot-segment de-rotation ----------------------------------------
+ * lib/pl_descrambler.cc:36-98   complex scrambling sequence of a Gold code: R_n in 0..3, descrambling factor
+ *                               conj(exp(j R_n pi/2)) = {1, -j, -1, +j}[R_n]
+ * lib/plsync_cc_impl.cc:639-802 handle_payload: descramble the whole payload (pilot blocks included in the index),
+ *                               then de-rotate the data slots: phase starts at -plheader_phase, advances by
+ *                               -2 pi fine_foffset per symbol (only when coarse corrected), and is reset to
+ *                               -pilot_phase[b - 1] at the start of every 16-slot segment b >= 1 (when coarse
+ *                               corrected); pilot blocks (36 symbols after every 16 slots) are dropped.
+ * The de-rotation is VOLK's volk_32fc_s32fc_x2_rotator_32fc (third party, absent, version unpinned by the reference);
+ * restated in its generic form: out = in * phase; phase *= inc; the phase re-normalised every 512 samples.  The
+ * serial float recurrence is not bit-reproducible by a parallel evaluation: parity of the de-rotation is to tolerance.
+ * The R_n sequence is pinned against lib/pl_descrambler.cc compiled unmodified (oracle/ref_harness.cc: ref_pl_rn). */
+static int pl_parity18(long a, long b)
+{
+    int c = 0;
+    a &= b;
+    for (int i = 0; i < 18; i++)
+        c += (int)((a >> i) & 1);
+    return c & 1;
+}
+void orc_pl_rn(int gold_code, uint8_t* rn, int n)
+{
+    long x = 0x00001, y = 0x3FFFF;
+    for (int k = 0; k < gold_code; k++) { /* the x register advanced by the Gold code */
+        const int xb = pl_parity18(x, 0x0081);
+        x >>= 1;
+        if (xb)
+            x |= 0x20000;
+    }
+    for (int i = 0; i < n; i++) {
+        const int xa = pl_parity18(x, 0x8050), xb = pl_parity18(x, 0x0081), xc = (int)(x & 1);
+        x >>= 1;
+        if (xb)
+            x |= 0x20000;
+        const int ya = pl_parity18(y, 0x04A1), yb = pl_parity18(y, 0xFF60), yc = (int)(y & 1);
+        y >>= 1;
+        if (ya)
+            y |= 0x20000;
+        rn[i] = (uint8_t)((((xa ^ yb) & 1) << 1) | ((xc ^ yc) & 1));
+    }
+}
+/* one PLFRAME payload [n_slots * 90 + n_pilots * 36][2] -> XFECFRAME symbols [n_slots * 90][2] */
+void orc_pl_payload(const float* payload, int n_slots, int has_pilots, const uint8_t* rn, float plheader_phase, float fine_foffset,
+                    int coarse_corrected, const float* pilot_phase, float* out)
+{
+    const float phase_inc = coarse_corrected ? (float)(2.0 * 3.14159265358979323846 * fine_foffset) : 0.0f;
+    const float inc_re = cosf(-phase_inc), inc_im = sinf(-phase_inc);
+    float ph_re = cosf(-plheader_phase), ph_im = sinf(-plheader_phase);
+    int in_idx = 0, produced = 0, blk = 0;
+    for (int slot = 0; slot < n_slots;) {
+        int slots = n_slots - slot;
+        if (has_pilots && slots > 16 - (slot % 16))
+            slots = 16 - (slot % 16);
+        if (has_pilots && coarse_corrected && blk > 0 && (slot % 16) == 0) {
+            ph_re = cosf(-pilot_phase[blk - 1]);
+            ph_im = sinf(-pilot_phase[blk - 1]);
+        }
+        const int len = slots * 90;
+        for (int k = 0; k < len; k++) { /* the rotator call on this slot sequence */
+            static const float lut[4][2] = { { 1, 0 }, { 0, -1 }, { -1, 0 }, { 0, 1 } };
+            const float ar = payload[2 * (in_idx + k)], ai = payload[2 * (in_idx + k) + 1];
+            const float* d = lut[rn[in_idx + k]];
+            const float yr = ar * d[0] - ai * d[1], yi = ar * d[1] + ai * d[0];
+            out[2 * (produced + k)] = yr * ph_re - yi * ph_im;
+            out[2 * (produced + k) + 1] = yr * ph_im + yi * ph_re;
+            const float nr = ph_re * inc_re - ph_im * inc_im, ni = ph_re * inc_im + ph_im * inc_re;
+            ph_re = nr, ph_im = ni;
+            if ((k + 1) % 512 == 0 || k + 1 == len) {
+                const float mag = hypotf(ph_re, ph_im);
+                ph_re /= mag, ph_im /= mag;
+            }
+        }
+        in_idx += len;
+        produced += len;
+        slot += slots;
+        if (has_pilots && (slot % 16) == 0 && slot < n_slots) { /* a pilot block follows every 16 slots (not the last) */
+            in_idx += 36;
+            blk++;
+        }
+    }
+}

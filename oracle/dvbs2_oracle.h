@@ -97,6 +97,14 @@ long orc_bbdeheader_work(orc_bbdeheader*, const uint8_t* in, int frames, uint8_t
 /* packet, error, bbframe, bbframe_drop, bbframe_gap counts */
 void orc_bbdeheader_counters(const orc_bbdeheader*, uint64_t* out5);
 
+/* ---- PL descrambler + pilot-segment de-rotation (lib/pl_descrambler.cc:36-98, lib/plsync_cc_impl.cc:639-802) ----
+ * rn[i] in 0..3: scrambling code of payload symbol i (pilot blocks included); descrambling factor {1, -j, -1, +j}[rn]. */
+void orc_pl_rn(int gold_code, uint8_t* rn, int n);
+/* payload [n_slots * 90 + n_pilots * 36][2] floats -> out [n_slots * 90][2]; n_pilots = (n_slots - 1) / 16 with pilots.
+ * De-rotation restates VOLK's generic rotator (serial float recurrence): compare to tolerance. */
+void orc_pl_payload(const float* payload, int n_slots, int has_pilots, const uint8_t* rn, float plheader_phase, float fine_foffset,
+                    int coarse_corrected, const float* pilot_phase, float* out);
+
 #ifdef __cplusplus
 }
 #endif

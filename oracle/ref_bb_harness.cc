@@ -12,6 +12,7 @@
 
 #include "bbdeheader_bb_impl.h"
 #include "bbdescrambler_bb_impl.h"
+#include "pl_descrambler.h"
 
 using namespace gr::dvbs2rx;
 
@@ -50,6 +51,28 @@ int ref_bbdeheader_work(void* h, const uint8_t* in, int n_in, uint8_t* out, int 
     return blk->general_work(n_out, ninput, ins, outs);
 }
 long ref_bbdeheader_consumed(void* h) { return (*static_cast<bbdeheader_bb::sptr*>(h))->shim_consumed; }
+/* lib/pl_descrambler.cc (compiled unmodified over oracle/shim/volk): the scrambling code R_n of the first n payload
+ * symbols of a Gold code, read back from the descrambling sequence (1 -> 0, -j -> 1, -1 -> 2, +j -> 3) */
+int ref_pl_rn(int gold_code, uint8_t* rn, int n)
+{
+    pl_descrambler d(gold_code);
+    std::vector<gr_complex> ones(n, gr_complex(1.0f, 0.0f));
+    d.descramble(ones.data(), (uint16_t)n);
+    const gr_complex* y = d.get_payload();
+    for (int i = 0; i < n; ++i) {
+        if (y[i] == gr_complex(1, 0))
+            rn[i] = 0;
+        else if (y[i] == gr_complex(0, -1))
+            rn[i] = 1;
+        else if (y[i] == gr_complex(-1, 0))
+            rn[i] = 2;
+        else if (y[i] == gr_complex(0, 1))
+            rn[i] = 3;
+        else
+            return -1;
+    }
+    return 0;
+}
 void ref_bbdeheader_counters(void* h, uint64_t* out5)
 {
     bbdeheader_bb::sptr& blk = *static_cast<bbdeheader_bb::sptr*>(h);

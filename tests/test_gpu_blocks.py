@@ -43,6 +43,9 @@ def blk(gpu):
     l.blk_bbdeheader_counters.argtypes = [_P, _P]
     l.blk_demap_make.restype = _P
     l.blk_demap_make.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+    l.blk_demap_make_apsk.restype = _P
+    l.blk_demap_make_apsk.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_char_p, C.c_int]
+    l.blk_apsk_points.argtypes = [C.c_int, C.c_int, _P, C.c_int]
     l.blk_demap_free.argtypes = [_P]
     l.blk_demap_work.argtypes = [_P, C.c_int, _P, _P, C.POINTER(C.c_int)]
     l.blk_demap_snr.argtypes = [_P]
@@ -175,3 +178,38 @@ def test_bb_blocks_against_oracle(blk, gpu, oracle):
     assert dict(zip(("packets", "errors", "bbframes", "dropped", "gaps"), [int(v) for v in c])) == o.counters()
     assert o.counters()["dropped"] == 1
     blk.blk_bbdeheader_free(hd)
+
+
+def test_demapper_block_apsk_opt_in(blk, gpu):
+    """16APSK / 32APSK are rejected by default (as the reference throws) and accepted behind the explicit opt-in:
+    the block then demaps with the table-driven demapper and the frames decode through LDPC + BCH."""
+    d = gpu
+    from dvbs2rx_b200 import apsk, vectors
+    err = C.create_string_buffer(128)
+    rng = np.random.default_rng(19)
+    for mod, fs, rate_name, esn0, pts_py in ((d.MOD_16APSK, 0, "C2_3", 10.5, apsk.points_16apsk(apsk.GAMMA_16APSK["C2_3"])),
+                                             (d.MOD_32APSK, 1, "C9_10", 17.5, apsk.points_32apsk(*apsk.GAMMA_32APSK["C9_10"]))):
+        rate = d.RATE[rate_name]
+        assert not blk.blk_demap_make(fs, rate, mod, err, 128) and err.value == b"Unsupported constellation"
+        # the C++ tables are the Python ones
+        pts = np.zeros((32, 2), np.float32)
+        n = blk.blk_apsk_points(mod, rate, pts.ctypes.data, pts.size)
+        assert n == pts_py.shape[0] and np.allclose(pts[:n], pts_py, atol=1e-6)
+        bits = n.bit_length() - 1
+        F = 3
+        msg, cw, info = vectors.encode_frames(0, fs, rate, F, rng)
+        offs = apsk.row_offsets(info.n_ldpc, bits)
+        iq, n0 = vectors.awgn(apsk.map_bits(cw, pts_py, offs), esn0, rng)
+        iq = np.ascontiguousarray(iq)
+        h = blk.blk_demap_make_apsk(fs, rate, mod, esn0, err, 128)
+        assert h, err.value
+        out = np.zeros((F, info.n_ldpc), np.int8)
+        consumed = C.c_int()
+        assert blk.blk_demap_work(h, out.size, iq.ctypes.data, out.ctypes.data, C.byref(consumed)) == out.size
+        assert consumed.value == F * (info.n_ldpc // bits)
+        code = d.Code(0, fs, rate)
+        assert np.array_equal(out, code.demap_table(pts_py, offs, iq, n0))  # the block is a thin shell over the C ABI
+        dec, trials, corr = code.fec_decode(llr=out, max_trials=25)
+        assert (trials >= 0).all() and np.array_equal(dec, msg)
+        code.close()
+        blk.blk_demap_free(h)
