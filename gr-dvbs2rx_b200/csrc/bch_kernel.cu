@@ -71,7 +71,6 @@ __device__ __forceinline__ uint32_t warp_xor(uint32_t v)
 }
 
 constexpr int kBchWarps = 32; // warps per (persistent) CTA
-constexpr uint16_t kLogZero = 0xffff;
 
 // shared-memory carve-up (dynamic): antilog [2^m] | logB [kMaxT][256] | sig [warps][kMaxT + 2][32] | S [warps][2 kMaxT]
 // | roots [warps][kMaxT + 1] (uint32) | nroots [warps] (int)
@@ -81,6 +80,8 @@ __host__ __device__ inline size_t bch_smem_bytes(int m)
            (size_t)kBchWarps * (kMaxT + 1) * 4 + (size_t)kBchWarps * 4;
 }
 
+// T = error-correction capability (8, 10 or 12 for DVB-S2): compile time, so that the per-syndrome code is straight line
+template <int T>
 __global__ void __launch_bounds__(kBchWarps * 32, 1) bch_decode_kernel(const BchLaunch p)
 {
     extern __shared__ __align__(16) uint8_t bch_smem[];
@@ -97,7 +98,8 @@ __global__ void __launch_bounds__(kBchWarps * 32, 1) bch_decode_kernel(const Bch
     gf.log = p.log;
     gf.m = p.m;
     gf.nz = (1u << p.m) - 1u;
-    const int n = p.n, k = p.k, t = p.t;
+    const int n = p.n, k = p.k;
+    constexpr int t = T;
     const int n_bytes = n >> 3, k_bytes = k >> 3;
 
     // ---- tables: antilog into shared memory, then B_a[b] = sum_kbit bit_kbit(b) alpha^(a (7 - kbit)) in the log domain
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(kBchWarps * 32, 1) bch_decode_kernel(const Bch
         for (int kb = 0; kb < 8; ++kb)
             if (b & (0x80u >> kb))
                 v ^= gf.alpha(gf.fold(a * (uint32_t)(7 - kb)));
-        s_logB[idx] = v ? __ldg(p.log + v) : kLogZero;
+        s_logB[idx] = v ? __ldg(p.log + v) : (uint16_t)0; // b = 0: masked by the caller
     }
     __syncthreads();
 
@@ -134,19 +136,19 @@ __global__ void __launch_bounds__(kBchWarps * 32, 1) bch_decode_kernel(const Bch
             ex[i] = gf.fold(a * (uint32_t)(n - 8 - 8 * lane)); // lane < n_bytes always (n_bytes >= 32)
             st[i] = gf.fold(a * 256u);                         // 32 bytes further on
         }
+        const uint32_t nz = gf.nz;
         for (int y = lane; y < n_bytes; y += 32) {
             const uint32_t byte = __ldg(cw + y);
             if (y < k_bytes)
                 msg[y] = (uint8_t)byte;
+            const uint32_t live = byte ? 0xffffu : 0u; // B_a[0] = 0 has no logarithm: its table entry is 0, the term is masked
 #pragma unroll
             for (int i = 0; i < kMaxT; ++i) {
                 if (i < t) {
-                    const uint32_t lb = s_logB[i * 256 + byte];
-                    if (lb != kLogZero) {
-                        const uint32_t e = lb + ex[i];
-                        S_odd[i] ^= gf.alpha(e >= gf.nz ? e - gf.nz : e);
-                    }
-                    ex[i] = ex[i] >= st[i] ? ex[i] - st[i] : ex[i] + gf.nz - st[i];
+                    const uint32_t e = (uint32_t)s_logB[i * 256 + byte] + ex[i];
+                    S_odd[i] ^= (uint32_t)s_antilog[min(e, e - nz)] & live; // unsigned: e - nz wraps when e < nz
+                    const uint32_t d = ex[i] - st[i];
+                    ex[i] = min(d, d + nz); // (ex - st) mod nz
                 }
             }
         }
@@ -245,20 +247,45 @@ __global__ void __launch_bounds__(kBchWarps * 32, 1) bch_decode_kernel(const Bch
                 step[j] = gf.fold(32u * (uint32_t)j);
             }
             const uint32_t e_end = (uint32_t)n + p.shorten; // inclusive
-            for (uint32_t e = e0; e <= e_end; e += 32) {
-                uint32_t res = 0;
+            bool dense = (L == T);
 #pragma unroll
-                for (int j = 0; j <= kMaxT; ++j) {
-                    if (on[j]) {
-                        res ^= gf.alpha(acc[j]);
-                        uint32_t a = acc[j] + step[j];
-                        acc[j] = a >= gf.nz ? a - gf.nz : a;
+            for (int j = 0; j <= T; ++j)
+                dense = dense && on[j];
+            if (dense) {
+                // the usual case of an uncorrectable word (and of t errors): all t + 1 coefficients present -- no predicates
+                uint32_t stm[T + 1];
+#pragma unroll
+                for (int j = 0; j <= T; ++j)
+                    stm[j] = step[j] - nz;
+                for (uint32_t e = e0; e <= e_end; e += 32) {
+                    uint32_t res = 0;
+#pragma unroll
+                    for (int j = 0; j <= T; ++j) {
+                        res ^= (uint32_t)s_antilog[acc[j]];
+                        acc[j] = min(acc[j] + step[j], acc[j] + stm[j]); // (acc + step) mod nz, unsigned
+                    }
+                    if (res == 0) {
+                        const int slot = atomicAdd(&s_nroots[warp], 1);
+                        if (slot <= kMaxT)
+                            s_roots[warp][slot] = e;
                     }
                 }
-                if (res == 0) {
-                    const int slot = atomicAdd(&s_nroots[warp], 1);
-                    if (slot <= kMaxT)
-                        s_roots[warp][slot] = e;
+            } else {
+                for (uint32_t e = e0; e <= e_end; e += 32) {
+                    uint32_t res = 0;
+#pragma unroll
+                    for (int j = 0; j <= kMaxT; ++j) {
+                        if (on[j]) {
+                            res ^= (uint32_t)s_antilog[acc[j]];
+                            const uint32_t a = acc[j] + step[j];
+                            acc[j] = min(a, a - nz);
+                        }
+                    }
+                    if (res == 0) {
+                        const int slot = atomicAdd(&s_nroots[warp], 1);
+                        if (slot <= kMaxT)
+                            s_roots[warp][slot] = e;
+                    }
                 }
             }
             __syncwarp();
@@ -294,15 +321,23 @@ cudaError_t bch_launch(const BchLaunch& p, cudaStream_t stream)
     if (p.t > kMaxT || p.m < 8 || p.m > 16 || (p.n >> 3) < 32)
         return cudaErrorInvalidValue;
     const size_t smem = bch_smem_bytes(p.m);
-    cudaError_t e = cudaFuncSetAttribute(bch_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess)
-        return e;
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int blocks = std::max(1, std::min(sms, (p.frames + kBchWarps - 1) / kBchWarps));
-    bch_decode_kernel<<<blocks, kBchWarps * 32, smem, stream>>>(p);
-    return cudaGetLastError();
+    const int blocks = std::max(1, std::min(sms, p.frames)); // frames go round the CTAs: every SM takes part
+    auto go = [&](auto kern) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess)
+            return e;
+        kern<<<blocks, kBchWarps * 32, smem, stream>>>(p);
+        return cudaGetLastError();
+    };
+    switch (p.t) {
+    case 8: return go(bch_decode_kernel<8>);
+    case 10: return go(bch_decode_kernel<10>);
+    case 12: return go(bch_decode_kernel<12>);
+    default: return cudaErrorInvalidValue; // lib/fec_params.cc knows no other t
+    }
 }
 
 // Forces the module that holds these kernels to be loaded now (CUDA loads lazily at the first launch, and that
@@ -312,7 +347,8 @@ cudaError_t bch_preload()
 {
     cudaFuncAttributes a;
     cudaError_t e;
-    if ((e = cudaFuncGetAttributes(&a, bch_decode_kernel)) != cudaSuccess)
+    if ((e = cudaFuncGetAttributes(&a, bch_decode_kernel<8>)) != cudaSuccess || (e = cudaFuncGetAttributes(&a, bch_decode_kernel<10>)) != cudaSuccess ||
+        (e = cudaFuncGetAttributes(&a, bch_decode_kernel<12>)) != cudaSuccess)
         return e;
     return cudaSuccess;
 }

@@ -29,6 +29,15 @@ __device__ __forceinline__ int convert_8i(float r)
     return __float2int_rn(r);
 }
 
+// the same in one instruction: round to nearest even, then saturate to int8 (identical for every finite input:
+// anything above 127 or below -128 ends at the rail either way); the low byte of the result is the int8
+__device__ __forceinline__ uint32_t convert_8i_sat(float r)
+{
+    int v;
+    asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(v) : "f"(r));
+    return (uint32_t)v & 0xffu;
+}
+
 __global__ void __launch_bounds__(256) demap_qpsk_kernel(const DemapLaunch p)
 {
     const int frame = blockIdx.y;
@@ -201,8 +210,7 @@ __global__ void __launch_bounds__(256, 3) demap_table_kernel(const TableDemapLau
 #pragma unroll
                 for (int i2 = 0; i2 < n; i2 += 2)
                     v[i2 >> 1] = fminf(v[i2], v[i2 + 1]);
-                const int q8 = convert_8i(__fmul_rn(__fsub_rn(d1, d0), inv_n0));
-                packed[k] |= (uint32_t)(uint8_t)q8 << (8 * u);
+                packed[k] |= convert_8i_sat(__fmul_rn(__fsub_rn(d1, d0), inv_n0)) << (8 * u);
             }
         }
 #pragma unroll

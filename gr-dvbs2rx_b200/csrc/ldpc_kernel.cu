@@ -231,7 +231,7 @@ __device__ __forceinline__ void chain_walk(uint8_t* __restrict__ L, const ChainR
 }
 
 #ifndef DVBS2_THREE_CTA_UPTO
-#define DVBS2_THREE_CTA_UPTO 13
+#define DVBS2_THREE_CTA_UPTO 25
 #endif
 // resident CTAs per SM the kernels are compiled for: three CTAs are 18 warps = 5 on some scheduler, whose register file
 // holds 16384 registers: 96 per thread at most

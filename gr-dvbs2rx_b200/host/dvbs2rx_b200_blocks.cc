@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -13,16 +14,30 @@ namespace gr {
 namespace dvbs2rx {
 
 namespace {
+// Device the blocks of this process are created on: set_device(), else the DVBS2RX_B200_DEVICE environment variable,
+// else 0.  Every block owns its handle (tables, streams, scratch): GNU Radio runs the blocks of a flowgraph in
+// different threads and a handle serves one thread at a time; sharing one between the demapper, LDPC and BCH blocks
+// would serialise them behind a lock for the sake of two table uploads of ~270 KB.
+int g_device = -1;
+int block_device()
+{
+    if (g_device >= 0)
+        return g_device;
+    const char* env = getenv("DVBS2RX_B200_DEVICE");
+    return env ? atoi(env) : 0;
+}
 dvbs2b200_code* create_code(int standard, int framesize, int rate)
 {
     dvbs2b200_code* h = nullptr;
-    int rc = dvbs2b200_code_create(&h, 0, standard, framesize, rate);
+    int rc = dvbs2b200_code_create(&h, block_device(), standard, framesize, rate);
     if (rc != DVBS2B200_OK)
         throw std::runtime_error(std::string("dvbs2b200: ") + dvbs2b200_last_error());
     return h;
 }
 const int DEFAULT_TRIALS = 25; // lib/ldpc_decoder_bb_impl.cc:391
 } // namespace
+
+void set_device(int device) { g_device = device; }
 
 // ---- ldpc_decoder_bb ------------------------------------------------------------------------------
 ldpc_decoder_bb::sptr ldpc_decoder_bb::make(dvb_standard_t standard, dvb_framesize_t framesize, dvb_code_rate_t rate,
@@ -438,7 +453,8 @@ int ldpc_dec_init(int standard, int framesize, int rate, int simd_size)
     ldpc_dec_shutdown();
     if (simd_size != 16 && simd_size != 32)
         return DVBS2B200_EINVAL;
-    int rc = dvbs2b200_code_create(&g_code, 0, standard, framesize, rate);
+    const char* env = getenv("DVBS2RX_B200_DEVICE");
+    int rc = dvbs2b200_code_create(&g_code, env ? atoi(env) : 0, standard, framesize, rate);
     if (rc != DVBS2B200_OK)
         return rc;
     dvbs2b200_code_info info;

@@ -41,6 +41,10 @@ namespace dvbs2rx {
 // reference's batch and keeps the reference's batch semantics inside it (term_group = 32).
 constexpr int kRefSimdSize = 32;
 
+// CUDA device the blocks created from now on live on (default: DVBS2RX_B200_DEVICE from the environment, else 0).
+// A flowgraph that wants several GPUs creates one chain of blocks per device, or calls dvbs2b200_multi_* directly.
+void set_device(int device);
+
 // What the reference publishes on "llr_pdu" (lib/ldpc_decoder_bb_impl.cc:362-367,422-429):
 // meta {simd_size, frame_cnt} + posterior LLRs of one SIMD batch.
 struct llr_pdu {
