@@ -216,7 +216,7 @@ int create_from_blob(dvbs2b200_code** out, int device, std::vector<uint8_t>&& bl
         return bail(cuda_fail(e, "kernel preload"));
     h->ldpc_smem = ldpc_smem_bytes(h->hdr.N, h->hdr.smem_bytes, h->hdr.chain_scratch, nullptr);
     if (h->hdr.max_cnt <= 28 && h->ldpc_smem <= (size_t)h->smem_optin)
-        h->ldpc_ctas = ldpc_ctas_per_sm(h->hdr.max_cnt, h->hdr.uniform_cnt != 0, h->ldpc_smem);
+        h->ldpc_ctas = ldpc_ctas_per_sm(h->hdr.N, h->hdr.max_cnt, h->hdr.uniform_cnt != 0, h->ldpc_smem);
     if (getenv("DVBS2B200_DEBUG"))
         fprintf(stderr, "[dvbs2b200] table %d: ldpc smem %zu B, %d CTAs/SM, %d state words per check-node pair\n", h->hdr.table,
                 h->ldpc_smem, h->ldpc_ctas, h->hdr.msg_words);
@@ -342,6 +342,7 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
     p.four = 4u;
     p.c30 = 1u << 30;
     p.c16 = 1u << 16;
+    p.c32 = 32u;
     p.neg1 = 0xffffffffu;
     if (p.group) {
         size_t words = (size_t)(frames / p.group) * (max_trials + 2);
@@ -371,9 +372,10 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
         CU(cudaStreamSynchronize(stream));
         CU(cudaMemcpy(host.data(), h->d_prof.p, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         if (FILE* f = fopen(prof_path, "w")) {
-            static const char* names[11] = { "load", "syndrome_pass", "pair_steps", "split_phase1", "split_serial_phase", "split_phase3",
-                                             "iteration_end", "output", "total", "n_pair_steps", "n_split_steps" };
-            for (int k = 0; k < 11; ++k) {
+            static const char* names[15] = { "load", "syndrome_pass", "pair_steps", "split_phase1", "level_serial_phase_thread0", "split_phase3",
+                                             "iteration_end", "output", "total", "n_pair_steps", "n_split_steps", "level_serial_phase_last_node",
+                                             "n_levels", "chain_serial_phase", "n_chain_nodes_per_walker" };
+            for (int k = 0; k < 15; ++k) {
                 double sum = 0;
                 for (int b = 0; b < grid; ++b)
                     sum += (double)host[(size_t)b * 16 + k];

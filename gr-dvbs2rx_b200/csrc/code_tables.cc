@@ -109,14 +109,13 @@ void build_schedule(const LdpcTableDef& def, Schedule& s)
             st.work_off = (uint32_t)s.order.size() | kStepSplit;
             for (int j = 0; j < 360; ++j)
                 s.order.push_back((uint16_t)level[j]);
-            // thread count of the named barrier in front of level l: the warps with nodes in level l-1 or l
-            // (thread p = j % 180 owns node j; levels rise with j)
-            std::vector<uint32_t> warps(depth + 2, 0);
-            for (int j = 0; j < 360; ++j)
-                warps[level[j]] |= 1u << ((j % 180) / 32);
+            // first node of each level (levels rise with j)
             s.order.push_back(0);
-            for (int lv = 1; lv <= depth; ++lv)
-                s.order.push_back((uint16_t)(32 * __builtin_popcount(warps[lv - 1] | warps[lv])));
+            for (int lv = 1, j = 0; lv <= depth + 1; ++lv) {
+                while (j < 360 && level[j] < lv)
+                    ++j;
+                s.order.push_back((uint16_t)j);
+            }
             // Chain form (code_tables.h): exactly two circulants (shifts a0 < a1) in one group.  With d = a1 - a0,
             // the bit node j reaches through link 0 is the bit node (j + d) mod 360 reaches through link 1, so
             // with delta = min(d, 360 - d) the layer is `delta` independent chains j, j + delta, j + 2 delta, ...
@@ -267,7 +266,6 @@ bool build_blob(int standard, int framesize, int rate, std::vector<uint8_t>& blo
     const LdpcTableDef& def = kLdpcTables[mc->table];
     Schedule s;
     build_schedule(def, s);
-
     BlobHeader h;
     memset(&h, 0, sizeof(h));
     h.magic = kBlobMagic;
@@ -300,7 +298,8 @@ bool build_blob(int standard, int framesize, int rate, std::vector<uint8_t>& blo
     h.uniform_cnt = (s.min_cnt == s.max_cnt) ? 1 : 0;
     h.bch_shorten = ((1u << h.gf_m) - 1) - (uint32_t)mc->nbch;
     h.split_steps = 1u;
-    h.chain_scratch = (uint32_t)std::max(s.has_chain ? 360 * 8 : 0, 180 * 4 * s.max_level_shared);
+    h.chain_scratch = (uint32_t)std::max(s.has_chain ? 360 * 8 : 0,
+                                         s.max_level_shared ? 720 * s.max_level_shared + 360 + (int)align16(2 * (s.max_depth + 2)) : 0);
     h.level_calls = 0u;
 
     size_t off = sizeof(BlobHeader);

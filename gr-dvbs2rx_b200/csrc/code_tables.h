@@ -29,7 +29,7 @@ const ModcodDef* find_modcod(int standard, int framesize, int rate);
 
 // ---- packed blob ---------------------------------------------------------------------------
 constexpr uint32_t kBlobMagic = 0x32425344u; // "DSB2"
-constexpr uint32_t kBlobVersion = 20;
+constexpr uint32_t kBlobVersion = 21;
 
 // One per layer, 8 bytes, lives in shared memory.
 struct LayerRec {
@@ -43,7 +43,7 @@ struct LayerRec {
 //     bit 30 of t = (p >= a')              ("ge": the rotation wrapped)
 //     bit 31 of t = ge ^ ra                ("g2": node p is the low byte)
 // so two multiply-high instructions give both, and the PRMT selectors depend on g2 alone (ldpc_core.cuh).
-struct EdgeRec {
+struct alignas(8) EdgeRec { // one 64-bit shared-memory load
     uint32_t w0;
     int32_t hi;
 };
@@ -69,7 +69,13 @@ constexpr uint32_t kStepOffMask = (1u << 24) - 1;
 // by exactly one check node.  Thread p keeps the pair mapping (check nodes p and p+180): it evaluates the
 // private links of both nodes in s16x2 like a conflict-free layer, then the shared links follow the serial order
 // of the reference (lib/ldpc_decoder/layered_decoder.hh:50-79), then the private links are updated.
-// StepRec::count = depth, work[] holds level[j] (1-based) for j = 0..359 and the barrier thread counts.
+// A node's level = 1 + the highest level among the earlier nodes that touch one of its bits; nodes of one level are
+// independent, and levels rise with j (the predecessors of node j are those of node j-1 moved up by one, plus
+// possibly one more), so a level is a range of j.  StepRec::count = depth; work[] holds level[j] (1-based) for
+// j = 0..359, then first_node[l] for l = 0..depth+1 (first_node[0] unused, first_node[depth+1] = 360).
+// Level form: the nodes of a level are handed out to the threads of the CTA (the node's private minimum, sign parity
+// and shared-link operands wait in shared memory, put there by the thread that owns the node), one block barrier per
+// level; the v->c values the nodes saw go back through shared memory to the owners for phase 3.
 // Chain form (one doubled group, the usual case): the serial order through the layer is `delta` independent
 // chains of nodes j, j + delta, ...; one lane walks one chain and hands the updated bit to the next node in a
 // register.  delta and the forwarding link ride in the step record.
@@ -95,7 +101,7 @@ struct BlobHeader {
     uint32_t bch_shorten;          // s = 2^m - 1 - nbch
     uint32_t split_steps;          // 1 (conflict layers are split steps)
     uint32_t chain_scratch;        // bytes of shared-memory scratch the split steps need (chain form: 360 x 8 B node records,
-                                   // level form: 180 x 4 B per shared link)
+                                   // level form: 720 B per shared link + 360 B + the first_node table, ldpc_steps.cuh: LevelScratch)
     uint32_t level_calls;          // unused (0)
 };
 static_assert(sizeof(BlobHeader) % 16 == 0, "header must keep sections 16-byte aligned");

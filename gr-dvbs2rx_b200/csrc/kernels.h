@@ -19,7 +19,7 @@ struct LdpcLaunch {
     // per-CTA check-node state, [grid][R/2 pairs x (1 + ceil(deg/8)) words] uint32, L2 resident
     uint32_t* msg_scratch;
     // two constants the compiler must not see through (they keep shifts / adds on the FMA pipe, ldpc_core.cuh)
-    uint32_t two, four, neg1, c30, c16;
+    uint32_t two, four, neg1, c30, c16, c32;
     // batch
     const int8_t* llr; // [frames][N], 4-byte aligned
     // streaming input: *ready counts the chunks of ready_chunk frames that have arrived (null: all there)
@@ -43,7 +43,7 @@ struct LdpcLaunch {
 size_t ldpc_smem_bytes(int N, uint32_t tab_bytes, uint32_t scratch_bytes, LdpcLaunch* p);
 cudaError_t ldpc_launch(const LdpcLaunch& p, int max_cnt, bool uniform, int grid, size_t smem, cudaStream_t stream);
 // resident CTAs per SM for this code's kernel instantiation (occupancy query)
-int ldpc_ctas_per_sm(int max_cnt, bool uniform, size_t smem);
+int ldpc_ctas_per_sm(int N, int max_cnt, bool uniform, size_t smem);
 
 struct BchLaunch {
     const uint8_t* cw; // [frames][n_bytes]

@@ -114,6 +114,7 @@ struct ThreadConst {
     uint32_t four; // on the FMA pipe instead of becoming shifts / adds on the (busier) ALU pipe
     uint32_t neg1;
     uint32_t c30, c16; // 1 << 30, 1 << 16: multiply-high by them = shift right by 2 / by 16
+    uint32_t c32;      // 32 (a literal 32 would become a shift-add on the ALU pipe)
 };
 struct LinkOp {
     uint32_t adr;  // byte offset of the halfword in L
@@ -221,7 +222,7 @@ LDPC_HD void link_sign(Acc<NW>& a, uint32_t xb, int d)
 template <int NW>
 LDPC_HD void link_merge(Acc<NW>& a, uint32_t xb, int d, const ThreadConst& tc)
 {
-    const uint32_t key = imad(link_mag(xb, tc), 32u, h2(d));
+    const uint32_t key = imad(link_mag(xb, tc), tc.c32, h2(d));
     a.k1 = vmin2(a.k1, vmax2(a.k0, key));
     a.k0 = vmin2(a.k0, key);
     link_sign(a, xb, d);

@@ -134,54 +134,51 @@ struct StateIo {
 };
 
 // ---- level form of a split step: the levels of the serial order -------------------------------------------
-// Levels rise with j, so the nodes of a warp sit in two contiguous level ranges (nodes p, nodes p+180).  A warp
-// only takes part in the levels it has nodes in.  Level l is entered through named barrier 1 + l % 15 whose
-// participants are the warps with nodes in level l-1 (their writes must be visible: they arrive, or sync if
-// they also have nodes in level l) and in level l (they sync); the host precomputed the thread count of each
-// barrier (level_tab[360 + l]).  A progress word keeps a warp that runs far ahead from re-using a barrier id
-// that an earlier level still owns.
-template <int CNT_MAX, int NW>
-__device__ __forceinline__ void level_phase(const FrameCtx& c, const ThreadConst& tc, int layer, bool active, int depth,
-                                            const uint16_t* __restrict__ level_tab, volatile int* progress, const uint32_t* ops,
-                                            SplitRegs<CNT_MAX, NW>& r)
+// The nodes of a level are independent and a level is a range of j (code_tables.h).  A node takes W = 2, 4, 8 or 16
+// neighbouring lanes, one per shared link (ldpc_steps.cuh: level_link_load / level_link_store); what it needs waits in
+// shared memory (level_prep), so it does not matter which lanes run it.  One block barrier per level.
+__device__ __forceinline__ void level_phase(uint8_t* L, int nshared, int depth, const LevelScratch& ls)
 {
-    int lvA = 0, lvB = 0;
-    if (active) {
-        lvA = (int)__ldg(level_tab + tc.p);
-        lvB = (int)__ldg(level_tab + tc.p + kPairs);
-    }
-    const int loA = (int)__reduce_min_sync(0xffffffffu, active ? (unsigned)lvA : 0xffffu);
-    const int hiA = (int)__reduce_max_sync(0xffffffffu, active ? (unsigned)lvA : 0u);
-    const int loB = (int)__reduce_min_sync(0xffffffffu, active ? (unsigned)lvB : 0xffffu);
-    const int hiB = (int)__reduce_max_sync(0xffffffffu, active ? (unsigned)lvB : 0u);
-    auto has_nodes = [&](int l) { return (l >= loA && l <= hiA) || (l >= loB && l <= hiB); };
-    int cnt_cur = (int)__ldg(level_tab + 360 + loA);
-    for (int lvl = loA; lvl <= hiB; ++lvl) {
-        if (!has_nodes(lvl)) {
-            lvl = loB - 1; // the gap between the two ranges
-            cnt_cur = (int)__ldg(level_tab + 360 + loB);
-            continue;
+    const int logw = nshared <= 2 ? 1 : nshared <= 4 ? 2 : nshared <= 8 ? 3 : 4;
+    const int lane = (int)threadIdx.x & 31, s = lane & ((1 << logw) - 1);
+    const unsigned gmask = ((1u << (1 << logw)) - 1u) << (lane - s); // the lanes of this node
+    const int slots = kLdpcThreads >> logw, slot = (int)threadIdx.x >> logw;
+    int j0 = (int)ls.first_node[1], j1 = (int)ls.first_node[2];
+    int rot = 0; // the warp that takes the first nodes of a level rotates: the serial phase loads all four schedulers
+    for (int lvl = 1; lvl <= depth; ++lvl) {
+        const int j2 = (int)ls.first_node[min(lvl + 2, depth + 1)];
+        int g = slot - rot;
+        g += g < 0 ? slots : 0;
+        for (int base = j0; base < j1; base += slots) {
+            const int j = base + g;
+            const bool mine = j < j1 && s < nshared;
+            const int hs = j >= kPairs ? 1 : 0, p = j - kPairs * hs;
+            LevelLink k;
+            k.key = kLevelNoKey;
+            k.xb = 255;
+            if (mine)
+                level_link_load(L, ls, p, hs, s, k);
+            // two smallest keys of the node: butterfly over its lanes, (smallest | second << 16) per lane.  (The
+            // warp-reduce instructions serialise sub-warp groups; shuffles do not care about groups.)
+            uint32_t v = k.key | 0x7fff0000u;
+#pragma unroll
+            for (int st = 0; st < 4; ++st) {
+                if (st < logw) {
+                    const uint32_t o = __shfl_xor_sync(0xffffffffu, v, 1 << st);
+                    const uint32_t mn = __vmins2(v, o), mx = __vmaxs2(v, o);
+                    v = (mn & 0xffffu) | (min(mx & 0xffffu, mn >> 16) << 16);
+                }
+            }
+            const uint32_t k0 = v & 0xffffu, k1 = v >> 16;
+            const uint32_t negs = (uint32_t)__popc(__ballot_sync(0xffffffffu, k.xb < 128) & gmask);
+            if (mine)
+                level_link_store(L, ls, p, hs, s, k, k0, k1, negs);
         }
-        const bool next_mine = has_nodes(lvl + 1);
-        const int cnt_next = (int)__ldg(level_tab + 360 + min(lvl + 1, depth));
-        if (lvl > 1) {
-            // A warp may get here long before the chain does.  The barrier id is shared with level lvl - 15:
-            // wait until that one has completed (progress = highest level known complete).
-            if (lvl > 15)
-                while (*progress < lvl - 16)
-                    __nanosleep(64);
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + lvl % 15), "r"(cnt_cur) : "memory");
-        }
-        if (active && lvA == lvl)
-            level_node<CNT_MAX, NW>(c, tc, layer, 0, ops, r);
-        if (active && lvB == lvl) // both nodes of the thread in one level: shallow layers only
-            level_node<CNT_MAX, NW>(c, tc, layer, 1, ops, r);
-        // hand over to level lvl + 1: if this warp has nodes there it syncs at the top of the loop
-        if (lvl < depth && !next_mine)
-            asm volatile("bar.arrive %0, %1;" ::"r"(1 + (lvl + 1) % 15), "r"(cnt_next) : "memory");
-        if (lvl > 1 && (threadIdx.x & 31) == 0)
-            atomicMax(const_cast<int*>(progress), lvl - 1);
-        cnt_cur = cnt_next;
+        __syncthreads();
+        j0 = j1;
+        j1 = j2;
+        rot += 32 >> logw;
+        rot = rot == slots ? 0 : rot;
     }
 }
 
@@ -230,14 +227,27 @@ __device__ __forceinline__ void chain_walk(uint8_t* __restrict__ L, const ChainR
     }
 }
 
+constexpr int kShortFrameBits = 16200;
+
 #ifndef DVBS2_THREE_CTA_UPTO
 #define DVBS2_THREE_CTA_UPTO 25
 #endif
+#ifndef DVBS2_FOUR_CTA_UPTO
+#define DVBS2_FOUR_CTA_UPTO 12 // wider check nodes spill too much at 80 registers
+#endif
+#ifndef DVBS2_SHORT_FRAME_REGS
+#define DVBS2_SHORT_FRAME_REGS 80
+#endif
 // resident CTAs per SM the kernels are compiled for: three CTAs are 18 warps = 5 on some scheduler, whose register file
-// holds 16384 registers: 96 per thread at most
+// holds 16384 registers: 96 per thread at most.  Short frames (SMALL: N <= 16200) leave shared memory for more CTAs and
+// spend more of their time in split steps (barrier waits), so they are compiled for four CTAs per SM: 80 registers.
+constexpr int ldpc_regs(int cnt_max, bool small_frame)
+{
+    return cnt_max > DVBS2_THREE_CTA_UPTO ? 168 : (small_frame && cnt_max <= DVBS2_FOUR_CTA_UPTO) ? DVBS2_SHORT_FRAME_REGS : 96;
+}
 
-template <int CNT_MAX, bool UNIFORM>
-__global__ void __launch_bounds__(kLdpcThreads) __maxnreg__(CNT_MAX <= DVBS2_THREE_CTA_UPTO ? 96 : 168) ldpc_decode_kernel(const LdpcLaunch p)
+template <int CNT_MAX, bool UNIFORM, bool SMALL>
+__global__ void __launch_bounds__(kLdpcThreads) __maxnreg__(ldpc_regs(CNT_MAX, SMALL)) ldpc_decode_kernel(const LdpcLaunch p)
 {
     constexpr int NW = (CNT_MAX + 2 + 7) / 8;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -250,7 +260,6 @@ __global__ void __launch_bounds__(kLdpcThreads) __maxnreg__(CNT_MAX <= DVBS2_THR
     uint8_t* const lin = smem + p.smem_rec_off; // byte 0 of a consumed node record (ldpc_steps.cuh)
     __shared__ int s_group_bad;
     __shared__ int s_abort;
-    __shared__ int s_progress; // level form: highest level of the current layer known to be complete
 
     const int tid = threadIdx.x;
     const int N = p.N, K = p.K, q = p.q, R = p.R;
@@ -265,6 +274,7 @@ __global__ void __launch_bounds__(kLdpcThreads) __maxnreg__(CNT_MAX <= DVBS2_THR
     tc.four = p.four;
     tc.c30 = p.c30;
     tc.c16 = p.c16;
+    tc.c32 = p.c32;
     tc.neg1 = p.neg1;
     const FrameCtx ctx = { L, layers, edges, K, q };
 
@@ -283,8 +293,10 @@ __global__ void __launch_bounds__(kLdpcThreads) __maxnreg__(CNT_MAX <= DVBS2_THR
 #ifdef DVBS2_PHASE_PROFILE
     // diagnostics build: cycles per phase, per CTA (thread 0) -> p.prof[blockIdx][16]:
     // 0 load, 1 syndrome pass, 2 pair steps, 3 split: phase 1, 4 split: serial phase, 5 split: phase 3, 6 iteration end,
-    // 7 output, 8 total, 9 pair steps (count), 10 split steps (count)
-    unsigned long long t_phase[12] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+    // 7 output, 8 total, 9 pair steps (count), 10 split steps (count), 11 level-form serial phase as the thread of node
+    // 359 sees it (entry to the last level done; written by thread 179), 12 levels walked (count), 13 chain-form serial
+    // phase (between its two block barriers), 14 chain nodes per walker (count)
+    unsigned long long t_phase[16] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
     const long long t_kernel = clock64();
     long long t_mark = t_kernel;
 #define LAP(slot)                                                   \
@@ -294,9 +306,11 @@ __global__ void __launch_bounds__(kLdpcThreads) __maxnreg__(CNT_MAX <= DVBS2_THR
         t_mark = now__;                                             \
     } while (0)
 #define COUNT(slot) (t_phase[slot] += 1)
+#define COUNTN(slot, n) (t_phase[slot] += (unsigned long long)(n))
 #else
 #define LAP(slot) ((void)0)
 #define COUNT(slot) ((void)0)
+#define COUNTN(slot, n) ((void)0)
 #endif
     for (int f = blockIdx.x; f < p.frames; f += gridDim.x) {
         // ---- streaming input: wait until the host->device copy of this frame's chunk has landed ----
@@ -434,18 +448,24 @@ __global__ void __launch_bounds__(kLdpcThreads) __maxnreg__(CNT_MAX <= DVBS2_THR
                         if ((tid >> 5) < ((delta + 31) >> 5))
                             chain_walk(L, rec, lin, delta, tid);
                         __syncthreads();
-                        LAP(4);
+                        LAP(13);
+                        COUNTN(14, depth);
                         if (active)
                             chain_p3_links<CNT_MAX, NW>(ctx, tc, out_link1, delta, lin, r);
                     } else {
+                        const int nshared = (int)layers[layer].conflict;
+                        const LevelScratch ls = level_scratch(rec, nshared);
                         if (active)
-                            level_prep<CNT_MAX, NW>(ctx, tc, layer, reinterpret_cast<uint32_t*>(rec), r);
-                        if (tid == 0)
-                            s_progress = 0;
+                            level_prep<CNT_MAX, NW>(ctx, tc, layer, ls, r);
+                        for (int i = tid; i < depth + 2; i += kLdpcThreads)
+                            ls.first_node[i] = __ldg(work + work_off + 360 + i);
                         __syncthreads();
                         LAP(3);
-                        level_phase<CNT_MAX, NW>(ctx, tc, layer, active, depth, work + work_off, &s_progress, reinterpret_cast<const uint32_t*>(rec), r);
+                        level_phase(L, nshared, depth, ls);
                         LAP(4);
+                        COUNTN(12, depth);
+                        if (active)
+                            level_p3_links<CNT_MAX, NW>(tc, nshared, ls, r);
                     }
                     if (active) {
                         Final<NW> fin;
@@ -456,11 +476,17 @@ __global__ void __launch_bounds__(kLdpcThreads) __maxnreg__(CNT_MAX <= DVBS2_THR
                         }
                         sio.store(layer, tid, out);
                     }
+                    if (last) {
+                        // the layer's posteriors are final once every thread has stored: the syndrome test of this one
+                        // layer can prove the frame still bad and save the pass over all layers
+                        __syncthreads();
+                        if (active)
+                            self_bad |= check_pair<CNT_MAX, UNIFORM>(ctx, tc, layer);
+                    }
                     LAP(5);
                     COUNT(10);
                 }
             }
-            // a split step at the end of the iteration leaves the proof to the syndrome pass
             proven_bad = __syncthreads_or(self_bad);
             LAP(6);
         }
@@ -514,16 +540,19 @@ __global__ void __launch_bounds__(kLdpcThreads) __maxnreg__(CNT_MAX <= DVBS2_THR
 #ifdef DVBS2_PHASE_PROFILE
     if (p.prof && tid == 0) {
         t_phase[8] = (unsigned long long)(clock64() - t_kernel);
-        for (int k = 0; k < 12; ++k)
-            p.prof[(size_t)blockIdx.x * 16 + k] = t_phase[k];
+        for (int k = 0; k < 16; ++k)
+            if (k != 11)
+                p.prof[(size_t)blockIdx.x * 16 + k] = t_phase[k];
     }
+    if (p.prof && tid == kPairs - 1)
+        p.prof[(size_t)blockIdx.x * 16 + 11] = t_phase[11];
 #endif
 }
 
-template <int CNT_MAX, bool UNIFORM>
+template <int CNT_MAX, bool UNIFORM, bool SMALL>
 cudaError_t launch_one(const LdpcLaunch& p, int grid, size_t smem, cudaStream_t stream)
 {
-    auto kern = ldpc_decode_kernel<CNT_MAX, UNIFORM>;
+    auto kern = ldpc_decode_kernel<CNT_MAX, UNIFORM, SMALL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess)
         return e;
@@ -535,10 +564,10 @@ cudaError_t launch_one(const LdpcLaunch& p, int grid, size_t smem, cudaStream_t 
     return cudaGetLastError();
 }
 
-template <int CNT_MAX, bool UNIFORM>
+template <int CNT_MAX, bool UNIFORM, bool SMALL>
 int occupancy_one(size_t smem)
 {
-    auto kern = ldpc_decode_kernel<CNT_MAX, UNIFORM>;
+    auto kern = ldpc_decode_kernel<CNT_MAX, UNIFORM, SMALL>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return 0;
     int n = 0;
@@ -595,15 +624,17 @@ size_t ldpc_smem_bytes(int N, uint32_t tab_bytes, uint32_t scratch_bytes, LdpcLa
 
 cudaError_t ldpc_launch(const LdpcLaunch& p, int max_cnt, bool uniform, int grid, size_t smem, cudaStream_t stream)
 {
-#define CALL(C, U) launch_one<C, U>(p, grid, smem, stream)
+    const bool small_frame = p.N <= kShortFrameBits;
+#define CALL(C, U) (small_frame ? launch_one<C, U, true>(p, grid, smem, stream) : launch_one<C, U, false>(p, grid, smem, stream))
     DVBS2_DISPATCH(CALL)
 #undef CALL
     return cudaErrorInvalidValue;
 }
 
-int ldpc_ctas_per_sm(int max_cnt, bool uniform, size_t smem)
+int ldpc_ctas_per_sm(int N, int max_cnt, bool uniform, size_t smem)
 {
-#define CALL(C, U) occupancy_one<C, U>(smem)
+    const bool small_frame = N <= kShortFrameBits;
+#define CALL(C, U) (small_frame ? occupancy_one<C, U, true>(smem) : occupancy_one<C, U, false>(smem))
     DVBS2_DISPATCH(CALL)
 #undef CALL
     return 0;

@@ -183,7 +183,7 @@ LDPC_HD void split_p1(const FrameCtx& c, const ThreadConst& tc, int layer, const
     }
 }
 
-// ---- level form: node (pair p, half hs) merges its shared links and updates those bits ---------------------
+// ---- level form: the nodes of a level, handed out to the threads of the CTA ---------------------------------
 // scalar view of one half of the accumulators
 template <int NW>
 LDPC_HD int half_nonneg(const Acc<NW>& a, int hs)
@@ -194,11 +194,32 @@ LDPC_HD int half_nonneg(const Acc<NW>& a, int hs)
         n += popc(sgn_word(a, w) & (hs ? 0x55550000u : 0x00005555u));
     return n;
 }
-// Operands of the shared links: addresses and old messages do not depend on what the predecessors do.  One word per
-// (shared link, pair) in the step's shared-memory scratch: byte address of node A's operand (node B's is that ^ 1:
-// the two bytes of one halfword) | -(old message) of node A << 16 | of node B << 24.
+// What the serial phase needs of a node does not depend on what its predecessors do, except the shared bits
+// themselves.  Phase 1 (thread p, nodes p and p+180) leaves it in the step's shared-memory scratch (LevelScratch):
+//   adr[s * 180 + p], s < nshared: byte address of node A's operand of shared link s (node B's is that ^ 1: the two
+//       bytes of one halfword)
+//   msg[s * 360 + 2p + hs]: -(old message) of the node through shared link s; the serial phase replaces it by the v->c
+//       value + 128 that the node saw, for phase 3
+//   nq[2p + hs]: the smallest magnitude of the node's private links, capped at 126, and in bit 7 the parity of its
+//       negative private v->c values
+//   first_node[l]: copy of the step's level table (code_tables.h)
+struct LevelScratch {
+    uint16_t* adr;
+    uint8_t* msg;
+    uint8_t* nq;
+    uint16_t* first_node;
+};
+LDPC_HD LevelScratch level_scratch(void* base, int nshared)
+{
+    LevelScratch ls;
+    ls.adr = reinterpret_cast<uint16_t*>(base);
+    ls.msg = reinterpret_cast<uint8_t*>(base) + 2 * kPairs * nshared;
+    ls.nq = ls.msg + 2 * kPairs * nshared;
+    ls.first_node = reinterpret_cast<uint16_t*>(ls.nq + 2 * kPairs);
+    return ls;
+}
 template <int CNT_MAX, int NW>
-LDPC_HD void level_prep(const FrameCtx& c, const ThreadConst& tc, int layer, uint32_t* ops, SplitRegs<CNT_MAX, NW>& r)
+LDPC_HD void level_prep(const FrameCtx& c, const ThreadConst& tc, int layer, const LevelScratch& ls, SplitRegs<CNT_MAX, NW>& r)
 {
     const LayerRec lr = c.layers[layer];
     const int nshared = (int)lr.conflict, d0 = 2 + r.npriv;
@@ -207,48 +228,56 @@ LDPC_HD void level_prep(const FrameCtx& c, const ThreadConst& tc, int layer, uin
         const LinkOp o = data_link(c.edges[lr.edge_begin + r.npriv + s], tc);
         const uint32_t wsh = pick_word(r.st.W, d >> 3) >> field_shift(d);
         const uint32_t no = prmt(r.st.candA, r.st.candB, imad(wsh & 0x0303u, 0x11u, 0xc480u));
-        ops[s * kPairs + (int)tc.p] = (o.adr + 1u - o.g2) | ((no & 0xffu) << 16) | ((no >> 16) << 24);
+        ls.adr[s * kPairs + (int)tc.p] = (uint16_t)(o.adr + 1u - o.g2);
+        reinterpret_cast<uint16_t*>(ls.msg)[s * kPairs + (int)tc.p] = (uint16_t)prmt(no, 0u, 0x4420u);
     }
+    const uint32_t qb = vmin2((r.acc.k0 >> 5) & 0x07ff07ffu, h2(126));
+    const uint32_t pnA = (uint32_t)((d0 - half_nonneg(r.acc, 0)) & 1), pnB = (uint32_t)((d0 - half_nonneg(r.acc, 1)) & 1);
+    reinterpret_cast<uint16_t*>(ls.nq)[(int)tc.p] = (uint16_t)((qb & 0x7fu) | (pnA << 7) | (((qb >> 16) & 0x7fu) << 8) | (pnB << 15));
 }
-// node (pair p, half hs) merges its shared links into its minima / signs and updates those bits
-template <int CNT_MAX, int NW>
-LDPC_HD void level_node(const FrameCtx& c, const ThreadConst& tc, int layer, int hs, const uint32_t* ops, SplitRegs<CNT_MAX, NW>& r)
+
+// One shared link s of one node (pair p, half hs) of the serial order: a lane of its own.  The dependent chain of a
+// level is what the serial phase costs (at the ~7 cycles per dependent instruction a lone warp gets on a busy SM), so
+// the links of a node sit in neighbouring lanes and meet in three warp reductions (ldpc_kernel.cu: level_phase; the
+// CPU emulation loops): the two smallest keys and the number of negative values over the node's shared links.
+struct LevelLink {
+    uint32_t adr; // byte address of the operand
+    int xb;       // v->c value + 128
+    uint32_t key; // max(|x| - 1, 0) * 32 + s
+    uint32_t nq;  // the node's private minimum (bits 0-6) and sign parity (bit 7)
+};
+constexpr uint32_t kLevelNoKey = 0x7fffu; // a lane without a link (keys are below 128 * 32)
+LDPC_HD void level_link_load(const uint8_t* L, const LevelScratch& ls, int p, int hs, int s, LevelLink& k)
 {
-    const LayerRec lr = c.layers[layer];
-    const int nshared = (int)lr.conflict, d0 = 2 + r.npriv;
-    int k0h = (int)((r.acc.k0 >> (16 * hs)) & 0xffffu), k1h = (int)((r.acc.k1 >> (16 * hs)) & 0xffffu);
-    int nn = half_nonneg(r.acc, hs);
-    // first pass: v->c values of the shared links as the predecessors left the bits
+    k.nq = ls.nq[2 * p + hs];
+    k.adr = (uint32_t)ls.adr[s * kPairs + p] ^ (uint32_t)hs;
+    const int no = (int)(int8_t)ls.msg[2 * kPairs * s + 2 * p + hs];
+    k.xb = clamp255((int)L[k.adr] + no);
+    k.key = (uint32_t)(mag_scalar(k.xb) * 32 + s);
+}
+// k0, k1: the two smallest keys over the node's shared links; negs: how many of them are negative (its parity counts).
+// The message to this link is the minimum over the node's OTHER links -- the private minimum and the other shared
+// links -- with the sign parity of the other links.
+LDPC_HD void level_link_store(uint8_t* L, const LevelScratch& ls, int p, int hs, int s, const LevelLink& k, uint32_t k0, uint32_t k1, uint32_t negs)
+{
+    const uint32_t q = k.nq & 0x7fu;
+    const uint32_t other = (k.key == k0 ? k1 : k0) >> 5;
+    const int m = (int)(other < q ? other : q);
+    const uint32_t isneg = k.xb < 128 ? 1u : 0u;
+    const uint32_t neg = ((k.nq >> 7) ^ negs ^ isneg) & 1u;
+    L[k.adr] = (uint8_t)clamp255(k.xb + (neg ? -m : m));
+    ls.msg[2 * kPairs * s + 2 * p + hs] = (uint8_t)k.xb;
+}
+
+// phase 3 of the level form: the shared links join the accumulators of the pair with the values the nodes saw
+template <int CNT_MAX, int NW>
+LDPC_HD void level_p3_links(const ThreadConst& tc, int nshared, const LevelScratch& ls, SplitRegs<CNT_MAX, NW>& r)
+{
+    const int d0 = 2 + r.npriv;
     for (int s = 0; s < nshared; ++s) {
-        const int d = d0 + s;
-        const uint32_t w = ops[s * kPairs + (int)tc.p];
-        const uint32_t a = (w & 0xffffu) ^ (uint32_t)hs;
-        const int xb = clamp255((int)c.L[a] + (int)(int8_t)(w >> (16 + 8 * hs)));
-        const int key = mag_scalar(xb) * 32 + d;
-        const int hi = k0h > key ? k0h : key;
-        k1h = k1h < hi ? k1h : hi;
-        k0h = k0h < key ? k0h : key;
-        nn += xb >= 128;
-        const uint32_t bit = (xb >= 128 ? 1u : 0u) << (8 + 2 * (d & 3) + 16 * hs);
-        or_word(r.acc.lo, d >> 3, (d & 7) < 4 ? bit : 0u);
-        or_word(r.acc.hi, d >> 3, (d & 7) < 4 ? 0u : bit);
+        const uint32_t v = reinterpret_cast<const uint16_t*>(ls.msg)[s * kPairs + (int)tc.p];
+        link_merge(r.acc, prmt(v, 0u, 0x4140u), d0 + s, tc);
     }
-    const int min0 = k0h >> 5 < 126 ? k0h >> 5 : 126, min1 = k1h >> 5 < 126 ? k1h >> 5 : 126;
-    const int arg = k0h & 31;
-    const int pn = (r.deg - nn) & 1; // parity of the negative v->c values of ALL links of the node
-    // second pass: the operands are still as read above (each is written once, here)
-    for (int s = 0; s < nshared; ++s) {
-        const int d = d0 + s;
-        const uint32_t w = ops[s * kPairs + (int)tc.p];
-        const uint32_t a = (w & 0xffffu) ^ (uint32_t)hs;
-        const int xb = clamp255((int)c.L[a] + (int)(int8_t)(w >> (16 + 8 * hs)));
-        const int m = (d == arg) ? min1 : min0;
-        const int neg = pn ^ (xb < 128 ? 1 : 0);
-        c.L[a] = (uint8_t)clamp255(xb + (neg ? -m : m));
-    }
-    const uint32_t keep = hs ? 0x0000ffffu : 0xffff0000u;
-    r.acc.k0 = (r.acc.k0 & keep) | ((uint32_t)k0h << (16 * hs));
-    r.acc.k1 = (r.acc.k1 & keep) | ((uint32_t)k1h << (16 * hs));
 }
 
 // ---- chain form ---------------------------------------------------------------------------------------------

@@ -37,7 +37,7 @@ static int run_frame(const LdpcTableDef& def, const Schedule& s, const int8_t* l
         L[pos_of_bit(n, K, R)] = (uint8_t)(llr[n] ^ 0x80);
     FrameCtx c{ L.data(), s.layers.data(), s.edges.data(), K, q };
     std::vector<RawState<NW>> state((size_t)q * kPairs);
-    std::vector<ChainRec> rec(360 + 180 * kMaxSharedLinks / 2);
+    std::vector<ChainRec> rec(4096); // the step's shared-memory scratch
     auto tconst = [](int p) {
         ThreadConst tc;
         tc.p = (uint32_t)p;
@@ -45,6 +45,7 @@ static int run_frame(const LdpcTableDef& def, const Schedule& s, const int8_t* l
         tc.four = 4u;
         tc.c30 = 1u << 30;
         tc.c16 = 1u << 16;
+        tc.c32 = 32u;
         tc.neg1 = 0xffffffffu;
         return tc;
     };
@@ -104,13 +105,33 @@ static int run_frame(const LdpcTableDef& def, const Schedule& s, const int8_t* l
                 for (int p = 0; p < kPairs; ++p)
                     chain_p3_links<CNT_MAX, NW>(c, tconst(p), out_link1, delta, reinterpret_cast<const uint8_t*>(rec.data()), regs[p]);
             } else {
+                const int nshared = (int)c.layers[layer].conflict;
+                LevelScratch ls = level_scratch(rec.data(), nshared);
+                const uint16_t* first_node = level + 360;
                 for (int p = 0; p < kPairs; ++p)
-                    level_prep<CNT_MAX, NW>(c, tconst(p), layer, reinterpret_cast<uint32_t*>(rec.data()), regs[p]);
+                    level_prep<CNT_MAX, NW>(c, tconst(p), layer, ls, regs[p]);
                 for (int lvl = 1; lvl <= depth; ++lvl)
-                    for (int p = 0; p < kPairs; ++p)
-                        for (int hs = 0; hs < 2; ++hs)
-                            if (level[p + kPairs * hs] == lvl)
-                                level_node<CNT_MAX, NW>(c, tconst(p), layer, hs, reinterpret_cast<const uint32_t*>(rec.data()), regs[p]);
+                    for (int j = first_node[lvl]; j < first_node[lvl + 1]; ++j) {
+                        if (level[j] != lvl) {
+                            printf("first_node table inconsistent\n");
+                            exit(1);
+                        }
+                        LevelLink k[kMaxSharedLinks];
+                        uint32_t k0 = kLevelNoKey, k1 = kLevelNoKey, negs = 0;
+                        for (int sl = 0; sl < nshared; ++sl) {
+                            level_link_load(L.data(), ls, j % kPairs, j / kPairs, sl, k[sl]);
+                            if (k[sl].key < k0) {
+                                k1 = k0;
+                                k0 = k[sl].key;
+                            } else if (k[sl].key < k1)
+                                k1 = k[sl].key;
+                            negs ^= k[sl].xb < 128 ? 1u : 0u;
+                        }
+                        for (int sl = 0; sl < nshared; ++sl)
+                            level_link_store(L.data(), ls, j % kPairs, j / kPairs, sl, k[sl], k0, k1, negs);
+                    }
+                for (int p = 0; p < kPairs; ++p)
+                    level_p3_links<CNT_MAX, NW>(tconst(p), nshared, ls, regs[p]);
             }
             // phase 3: every thread finalizes first (reads), then stores -- the kernel has no barrier in between,
             // and needs none: see ldpc_kernel.cu

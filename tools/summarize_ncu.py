@@ -81,6 +81,25 @@ def main():
             json.dump({"kernel": name, "report": rep, "dram_bytes_per_launch": t,
                        "dram_read": to_bytes("dram__bytes_read.sum"), "dram_write": to_bytes("dram__bytes_write.sum"),
                        "note": "one bench launch = 2664 frames x 68,850 B (soft input + packed hard decisions) = 183,416,400 algorithmic bytes"}, f, indent=1)
+        # the issue-side roofline of the LDPC kernel (bench.py copies it into `roofline_issue`): the kernel is bound by
+        # instruction issue / the ALU pipe, not by HBM
+        def num(key):
+            return float(m[key][1].replace(",", "")) if key in m else None
+        inst = num("smsp__inst_executed.sum")
+        edges = 2664 * 25 * 226799  # the bench launch: frames x iterations x edge updates of DVB-S2 1/2 normal
+        with open("profiles/ldpc_issue.json", "w") as f:
+            json.dump({"kernel": name, "report": rep, "bound": "issue",
+                       "achieved": num("sm__inst_executed.avg.per_cycle_elapsed"), "peak": 4.0, "unit": "warp instructions / cycle / SM",
+                       "frac": (num("sm__inst_executed.avg.per_cycle_elapsed") or 0) / 4.0,
+                       "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                       "alu_pipe_pct": num("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                       "fma_pipe_pct": num("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                       "warp_instructions_per_launch": inst,
+                       "thread_instructions_per_edge_update": inst * 32.0 / edges if inst else None,
+                       "stall_barrier_per_issue": num("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"),
+                       "stall_math_pipe_throttle_per_issue": num("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"),
+                       "note": "ncu --set full of one bench-sized launch (2664 frames, 25 iterations); numbers under the profiler, "
+                               "the frame rate is bench.py's"}, f, indent=1)
     print("\n".join(lines[:45]))
 
 
