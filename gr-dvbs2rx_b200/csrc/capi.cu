@@ -584,6 +584,9 @@ int bb_deheader_dev(dvbs2b200_code* h, const uint8_t* d_bb, int frames, int scra
         return fail(DVBS2B200_EINVAL, "null buffer");
     if ((uintptr_t)d_ts & 3)
         return fail(DVBS2B200_EINVAL, "ts buffer must be 4-byte aligned");
+    // a smaller buffer would lose packets while the deheader state advances past them: refuse before anything moves
+    if (ts_cap < bb_ts_capacity(h->hdr, frames))
+        return fail(DVBS2B200_EINVAL, "ts buffer smaller than dvbs2b200_bb_ts_capacity(frames)");
     if ((rc = h->d_bbrec.ensure((size_t)frames * sizeof(uint32_t))) || (rc = h->d_bbplan.ensure((size_t)frames * sizeof(BbPlan))))
         return rc;
     BbLaunch p;
@@ -1666,7 +1669,9 @@ int dvbs2b200_bb_deheader(dvbs2b200_code* h, const uint8_t* bbframes, int frames
     DeviceGuard g(h->device);
     StreamOrder so(h, h->stream);
     const size_t bytes = (size_t)frames * (h->hdr.kbch / 8);
-    const size_t cap = std::min(ts_cap, bb_ts_capacity(h->hdr, frames));
+    const size_t cap = bb_ts_capacity(h->hdr, frames);
+    if (ts_cap < cap)
+        return fail(DVBS2B200_EINVAL, "ts buffer smaller than dvbs2b200_bb_ts_capacity(frames)");
     int rc;
     if ((rc = h->d_mid.ensure(bytes)) || (rc = h->d_ts.ensure(cap + 256)))
         return rc;
@@ -1770,7 +1775,9 @@ int dvbs2b200_fec_decode_ts(dvbs2b200_code* h, int constellation, const float* i
     if (iq && !bits)
         return fail(DVBS2B200_EUNSUPPORTED, "Unsupported constellation");
     const size_t in_bytes = (size_t)frames * (iq ? (size_t)(hd.N / bits) * 8 : (size_t)hd.N);
-    const size_t cap = std::min(ts_cap, bb_ts_capacity(hd, frames));
+    const size_t cap = bb_ts_capacity(hd, frames);
+    if (ts_cap < cap)
+        return fail(DVBS2B200_EINVAL, "ts buffer smaller than dvbs2b200_bb_ts_capacity(frames)");
     int rc;
     if ((rc = h->d_in.ensure(in_bytes)) || (rc = h->d_ts.ensure(cap + 256)) || (rc = h->d_i32a.ensure((size_t)frames * 4)) ||
         (rc = h->d_i32b.ensure((size_t)frames * 4)))

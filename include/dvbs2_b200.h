@@ -246,7 +246,8 @@ int dvbs2b200_fec_decode_dev(dvbs2b200_code* h, int constellation, const float* 
  * a TS packet cut by a BBFRAME boundary carry over from call to call in the handle (device memory), exactly
  * the reference block's members; dvbs2b200_bb_reset() puts it back to the just-constructed state.
  * ts receives whole 188-byte packets (sync byte restored, transport-error indicator set on a CRC-8 failure);
- * dvbs2b200_bb_ts_capacity(frames) bytes always suffice.  scrambled != 0: the input is BCH output and is
+ * dvbs2b200_bb_ts_capacity(frames) bytes always suffice and are required: a smaller ts_cap is DVBS2B200_EINVAL and
+ * nothing is consumed (a clipped batch would lose packets while the deheader state moves past them).  scrambled != 0: the input is BCH output and is
  * descrambled on the fly (bbdescrambler_bb fused in); 0: already descrambled, as the reference block expects.
  * One deviation: where the reference's unsigned arithmetic wraps and reads past the BBFRAME (re-synchronising
  * on a header with syncd == dfl, lib/bbdeheader_bb_impl.cc:203-209), that frame yields no packet here. */

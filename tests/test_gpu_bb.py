@@ -153,3 +153,23 @@ def test_deheader_random_headers_match_oracle(gpu, oracle):
             assert got.size == want.size and np.array_equal(got, want), (seed, lo, hi)
         assert code.bb_counters() == o.counters(), seed
     code.close()
+
+
+def test_deheader_refuses_a_ts_buffer_below_capacity(gpu):
+    """A clipped batch would lose packets while the deheader state moves on: EINVAL, nothing consumed."""
+    import ctypes as C
+    d = gpu
+    code = d.Code(0, 1, d.RATE["C1_2"])
+    rng = np.random.default_rng(3)
+    up = bbf.ts_packets(400, rng)
+    bb = bbf.bbframe_stream(code.kbch, 8, up)
+    cap = code.bb_ts_capacity(8)
+    ts = np.zeros(cap, dtype=np.uint8)
+    n = C.c_size_t(7)
+    rc = d.lib().dvbs2b200_bb_deheader(code._h, bb.ctypes.data, 8, 0, ts.ctypes.data, cap - 188, C.byref(n))
+    assert rc == -1 and n.value == 0  # DVBS2B200_EINVAL
+    assert b"capacity" in d.lib().dvbs2b200_last_error()
+    assert code.bb_counters()["bbframes"] == 0
+    got = code.bb_deheader(bb)  # the same frames go through afterwards
+    assert got.size > 0 and got.size % 188 == 0
+    code.close()

@@ -136,9 +136,21 @@ def test_sharding_under_gloo_world_size_2(built, tmp_path):
     assert a[2] == b[2] == "100"   # all-reduced frame counter
 
 
+def _split_steps(blob):
+    """(layer, delta, depth, flags, work offset) of the split steps of a table blob, and its work[] array."""
+    hdr = np.frombuffer(blob[:160].tobytes(), dtype=np.uint32)
+    n_steps, step_off, order_off = int(hdr[22]), int(hdr[32]), int(hdr[33])
+    raw = blob[step_off:step_off + 8 * n_steps].tobytes()
+    steps = np.frombuffer(raw, dtype=np.dtype([("layer", "u1"), ("run_len", "u1"), ("count", "<u2"), ("work_off", "<u4")]))
+    work = np.frombuffer(blob[order_off:int(hdr[34])].tobytes(), dtype=np.uint16)
+    return [(int(s["layer"]), int(s["run_len"]), int(s["count"]), int(s["work_off"]) >> 24, int(s["work_off"]) & 0xffffff)
+            for s in steps if s["count"]], work
+
+
 def test_split_schedule_covers_every_table(built):
-    """Every conflict layer of the 57 tables has at most kMaxSharedLinks (12) shared links, so the split
-    form of the schedule exists for all of them; both forms of the blob build and validate."""
+    """Every conflict layer of the 57 tables has at most kMaxSharedLinks (12) shared links.  The level table of a
+    split step: levels start at 1, never fall with j (the kernel hands out a level as a RANGE of nodes), and
+    first_node[] marks exactly those ranges.  Holds with and without the chain form (DVBS2B200_CHAIN=0)."""
     import dvbs2rx_b200 as d
     from collections import Counter
     worst = 0
@@ -148,18 +160,32 @@ def test_split_schedule_covers_every_table(built):
             c = Counter(grp[lay == layer].tolist())
             worst = max(worst, sum(v for v in c.values() if v > 1))
     assert worst == 12
-    old = os.environ.get("DVBS2B200_SPLIT")
+    old = os.environ.get("DVBS2B200_CHAIN")
     try:
-        for mode in ("0", "1"):
-            os.environ["DVBS2B200_SPLIT"] = mode
-            for fs, rate in ((1, "C1_2"), (1, "C9_10"), (0, "C8_9"), (0, "C2_3")):
+        for mode in (None, "0"):
+            if mode is None:
+                os.environ.pop("DVBS2B200_CHAIN", None)
+            else:
+                os.environ["DVBS2B200_CHAIN"] = mode
+            seen_chain = False
+            for fs, rate in ((1, "C1_2"), (1, "C3_4"), (1, "C9_10"), (0, "C8_9"), (0, "C2_3")):
                 blob = d.build_tables(0, fs, d.RATE[rate])
-                assert blob.size > 1000
+                steps, work = _split_steps(blob)
+                assert steps
+                for layer, delta, depth, flags, off in steps:
+                    seen_chain |= bool(flags & 0x80)
+                    level = work[off:off + 360].astype(int)
+                    first = work[off + 360:off + 360 + depth + 2].astype(int)
+                    assert level[0] == 1 and level.max() == depth and (np.diff(level) >= 0).all(), (rate, layer)
+                    assert first[depth + 1] == 360
+                    for lv in range(1, depth + 1):
+                        assert (level[first[lv]:first[lv + 1]] == lv).all() and first[lv] < first[lv + 1], (rate, layer, lv)
+            assert seen_chain == (mode is None)
     finally:
         if old is None:
-            os.environ.pop("DVBS2B200_SPLIT", None)
+            os.environ.pop("DVBS2B200_CHAIN", None)
         else:
-            os.environ["DVBS2B200_SPLIT"] = old
+            os.environ["DVBS2B200_CHAIN"] = old
 
 
 def test_mixed_batch_sharding(built):

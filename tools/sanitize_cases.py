@@ -3,7 +3,8 @@
 
 Cases (each compared with nothing here -- parity is the test suite's job; the sanitizer is the judge):
   pair      QPSK 1/2 normal   pair steps + chain-form split steps, per-frame stop
-  level     9/10 normal       level-form split steps (named barriers, progress word), wide state
+  level     9/10 normal       level-form split steps (node operands through shared memory, lane per shared link,
+                              shuffle butterfly, block barrier per level), wide state
   short     2/3 short         chain and level form on a short frame
   c34       3/4 normal        chain + level mix, two CTAs per SM
   group     1/2 short         group-of-32 termination (cooperative launch, arrival counters), frames = 2 x resident CTAs
