@@ -196,7 +196,7 @@ def run_reference(args):
     fps, ms, kind, threads = cpu_reference_run(frames, args.steps, args.warmup, threads, MIXED_MODCODS if mixed else None)
     nf = frames * (len(MIXED_MODCODS) if mixed else 1)
     sample = "%d frames per step (32-frame AVX2 batches%s), %d host threads" % (nf, ", five single-code runs" if mixed else "", threads)
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "FECFRAMEs/s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
@@ -390,7 +390,7 @@ def run_ours(args):
             fps, ms, kind, threads = cpu_reference_run(frames, 3, 1, threads)
             out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
                                    "sample": "%d frames x 3 passes of the same workload" % frames}
-        print(json.dumps(out))
+        emit(json.dumps(out))
     code.close()
     if world > 1:
         dist.destroy_process_group()
@@ -547,13 +547,28 @@ def run_ours_mixed(args, torch, dist, d, world, rank, local, dev):
             "parity": {"sampled_frames_vs_per_code_oracle": chk, "mismatches": mism, "converged_frames": conv, "frames": tot,
                        "converged_frames_differing_from_sent": sbad},
         }
-        print(json.dumps(out))
+        emit(json.dumps(out))
     mixed.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's real stdout; everything else written to fd 1 while the run was on
+    (NCCL's version banner, a library's printf) went to stderr."""
+    data = (line + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line + "\n")
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    global _RESULT_FD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -566,6 +581,9 @@ def main():
                     help="c1: skip the end-to-end legs (for a launch list under ncu: the host path overlaps copies with a "
                          "persistent kernel, which a profiler that serialises kernels stalls until the kernel's bounded wait gives up)")
     args = ap.parse_args()
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         # the checker libraries only (oracle/ and oracle/_ref); the product library is neither built nor loaded here
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
