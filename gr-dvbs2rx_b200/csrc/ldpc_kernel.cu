@@ -7,7 +7,8 @@
 //   lib/ldpc_decoder_bb_impl.cc:432-442         hard decision + MSB-first packing
 //
 // Design (B200-first, not a translation of the SIMD-across-frames CPU code):
-//   * one FECFRAME per CTA of 192 threads, three CTAs per SM, persistent over the batch;
+//   * one FECFRAME per CTA of 192 threads, persistent over the batch; three CTAs per SM for normal frames (two
+//     for 28 data links per check node), four for short frames;
 //   * the frame's N posteriors stay in shared memory for the whole decode as biased bytes, in the
 //     pair-interleaved order of code_tables.h: check nodes p and p+180 of a layer read / write ONE aligned 16-bit
 //     word per link, so a thread runs TWO check nodes in the halves of a 32-bit register (s16x2);
@@ -149,7 +150,10 @@ __device__ __forceinline__ void level_phase(uint8_t* L, int nshared, int depth, 
         const int j2 = (int)ls.first_node[min(lvl + 2, depth + 1)];
         int g = slot - rot;
         g += g < 0 ? slots : 0;
+        const int g_warp = g - (lane >> logw); // the warp's first slot: its slots do not wrap (rot is a multiple of them)
         for (int base = j0; base < j1; base += slots) {
+            if (base + g_warp >= j1)
+                continue; // no node for this warp: straight to the barrier (warp-uniform, the shuffles below stay converged)
             const int j = base + g;
             const bool mine = j < j1 && s < nshared;
             const int hs = j >= kPairs ? 1 : 0, p = j - kPairs * hs;

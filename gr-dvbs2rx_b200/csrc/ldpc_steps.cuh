@@ -4,10 +4,13 @@
 //   split_*      layer whose circulants share a 360-bit group (order sensitive in the reference, which visits the
 //                check nodes serially: lib/ldpc_decoder/layered_decoder.hh:50-79):
 //                  split_p1     private links of both nodes in s16x2 -> partial minima / signs
-//                  level form   level_node(): the node's shared links, at the node's level of the serial order
-//                  chain form   chain_p1() writes a record per node, chain_first() / chain_next() walk a chain and
-//                               hand the updated bit on in a register, chain_p3_links() redoes the shared links in
-//                               s16x2 with the inputs the walk saw
+//                  level form   level_prep() leaves what the serial phase needs of nodes p, p+180 in shared memory;
+//                               level_link_load() / level_link_store(): one shared link of one node, run by any
+//                               lane at the node's level of the serial order; level_p3_links() merges the values
+//                               the nodes saw into the pair's accumulators
+//                  chain form   chain_p1() writes a record per node, chain_node() walks a chain and hands the
+//                               updated bit on in a register, chain_p3_links() redoes the shared links in s16x2
+//                               with the inputs the walk saw
 //                  split_p3     final minima / signs -> new state, private (and, chain form, shared) links updated
 // The kernel puts the barriers between these calls; tools/ldpc_emul.cc runs them thread by thread.
 #pragma once
