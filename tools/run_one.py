@@ -7,6 +7,7 @@
     python tools/run_one.py snr   C3_5 1 6.2 0 2664      # SNR estimate (8PSK for 3/5, else QPSK) + demap
     python tools/run_one.py mixed C1_2 1 0 25 5000       # five MODCODs interleaved in one batch (host API)
     python tools/run_one.py apsk  C9_10 1 17.5 0 2664    # table-driven demapper (32APSK for 8/9, 9/10, else 16APSK)
+    python tools/run_one.py pl    C1_2 1 0 0 2664        # PL descrambler + pilot de-rotation (QPSK normal frame with pilots)
 
 Prints device time per pass (CUDA events) and the derived rates; not the bench line."""
 import os
@@ -152,3 +153,20 @@ elif what == "snr":
     print("snr %s: symbols-only %.1f us (%.0f GB/s), demap %.1f us (%.0f GB/s), with LLR %.1f us (%.0f GB/s); mean %.2f dB" % (
         rate_name, t1 * 1e6, iq_bytes / t1 / 1e9, t2 * 1e6, (iq_bytes + F * info.n_ldpc) / t2 / 1e9, t3 * 1e6,
         (iq_bytes + F * info.n_ldpc) / t3 / 1e9, float(10 * np.log10(d_snr.cpu().numpy().mean()))))
+elif what == "pl":
+    # PL descrambler + pilot de-rotation: QPSK normal frame with pilots (360 slots, 22 pilot blocks)
+    n_slots, pilots = 360, 1
+    plen = d.PlDescrambler.payload_len(n_slots, pilots)
+    pl = d.PlDescrambler(0, 0)
+    d_pay = torch.randn((F, plen, 2), dtype=torch.float32, device=dev)
+    finfo = np.zeros(F, dtype=d.PL_FRAME_DTYPE)
+    finfo["plheader_phase"] = rng.uniform(-3, 3, F)
+    finfo["fine_foffset"] = rng.uniform(-1e-4, 1e-4, F)
+    finfo["coarse_corrected"] = 1
+    finfo["pilot_phase"] = rng.uniform(-3, 3, (F, 22))
+    d_info = torch.from_numpy(finfo.view(np.uint8)).to(dev)
+    d_out = torch.empty((F, n_slots * 90, 2), dtype=torch.float32, device=dev)
+    t = timed(lambda: pl.process_dev(d_pay.data_ptr(), F, n_slots, pilots, d_info.data_ptr(), d_out.data_ptr(), stream), reps=10)
+    nbytes = F * (plen + n_slots * 90) * 8
+    print("pl: %.1f us per %d PLFRAME payloads (QPSK normal, pilots), %.0f GB/s of symbols in + out, %.2f M frames/s" % (
+        t * 1e6, F, nbytes / t / 1e9, F / t / 1e6))
