@@ -370,12 +370,21 @@ __global__ void __launch_bounds__(kLdpcThreads) __maxnreg__(ldpc_regs(CNT_MAX, S
         int proven_bad = 0;
         for (;;) {
             if (!proven_bad) {
-                int flag = 0;
-                if (active) {
-                    for (int i = 0; i < q; ++i)
-                        flag |= check_pair<CNT_MAX, UNIFORM>(ctx, tc, i);
+                // bad(): any unsatisfied check.  A frame that is still bad shows it within a few layers, so the pass
+                // goes over the layers in chunks and stops at the first chunk with an unsatisfied check.
+                constexpr int kSyndromeChunk = 8;
+                bad = 0;
+#pragma unroll 1
+                for (int i0 = 0; i0 < q && !bad; i0 += kSyndromeChunk) {
+                    int flag = 0;
+                    if (active) {
+                        const int i1 = min(i0 + kSyndromeChunk, q);
+#pragma unroll 1
+                        for (int i = i0; i < i1; ++i)
+                            flag |= check_pair<CNT_MAX, UNIFORM>(ctx, tc, i);
+                    }
+                    bad = __syncthreads_or(flag);
                 }
-                bad = __syncthreads_or(flag);
                 LAP(1);
             } else {
                 bad = 1;
