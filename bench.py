@@ -338,7 +338,7 @@ def run_ours(args):
         return world * F * steps / float(dt.item())
 
     e2e_steps = max(3, min(args.steps, 10))
-    e2e_value = e2e_pageable = None
+    e2e_value = e2e_pageable = e2e_registered = None
     if not args.device_only:
         e2e_value = e2e_run(h_llr.data_ptr(), h_msg.data_ptr(), h_trials.data_ptr(), h_corr.data_ptr(), e2e_steps)
         assert torch.equal(h_msg, d_msg.cpu()), "host-API result differs from the device-resident path"
@@ -348,6 +348,15 @@ def run_ours(args):
         p_tr, p_co = np.empty(F, dtype=np.int32), np.empty(F, dtype=np.int32)
         e2e_pageable = e2e_run(llr_np.ctypes.data, p_msg.ctypes.data, p_tr.ctypes.data, p_co.ctypes.data, e2e_steps)
         assert np.array_equal(p_msg, h_msg.numpy()), "pageable-buffer result differs from the pinned-buffer one"
+        # ... and with the same buffers page-locked in place once (dvbs2b200_host_register: what a block does with its
+        # ring buffers in start()); the registration is outside the timed region, as it is outside general_work
+        for a in (llr_np, p_msg, p_tr, p_co):
+            d.host_register(a)
+        p_msg[:] = 0
+        e2e_registered = e2e_run(llr_np.ctypes.data, p_msg.ctypes.data, p_tr.ctypes.data, p_co.ctypes.data, e2e_steps)
+        for a in (llr_np, p_msg, p_tr, p_co):
+            d.host_unregister(a)
+        assert np.array_equal(p_msg, h_msg.numpy()), "registered-buffer result differs from the pinned-buffer one"
     # clocks / throttle reasons sampled while the GPU was busy: the timed region and the end-to-end loops after it
     sampler.window(t_load0, time.perf_counter())
     clocks = sampler.stop() if rank == 0 else None
@@ -375,6 +384,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": world * F * N,
                     "d2h_bytes_per_step": world * F * (kb + 8), "buffers": "pinned host"},
             "e2e_pageable": {"value": e2e_pageable, "unit": "frames/s", "buffers": "pageable host (staged through the handle's pinned ring)"},
+            "e2e_registered": {"value": e2e_registered, "unit": "frames/s",
+                               "buffers": "the same pageable buffers page-locked in place once (dvbs2b200_host_register)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "ldpc_decode_kernel", "achieved": achieved, "peak": peak,

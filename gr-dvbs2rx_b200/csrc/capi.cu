@@ -642,6 +642,22 @@ int dvbs2b200_device_count(void)
     return n;
 }
 
+int dvbs2b200_host_register(void* ptr, size_t bytes)
+{
+    if (!ptr || bytes == 0)
+        return fail(DVBS2B200_EINVAL, "null buffer");
+    CU(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return DVBS2B200_OK;
+}
+
+int dvbs2b200_host_unregister(void* ptr)
+{
+    if (!ptr)
+        return fail(DVBS2B200_EINVAL, "null buffer");
+    CU(cudaHostUnregister(ptr));
+    return DVBS2B200_OK;
+}
+
 int dvbs2b200_num_tables(void) { return num_tables(); }
 const char* dvbs2b200_table_name(int table)
 {

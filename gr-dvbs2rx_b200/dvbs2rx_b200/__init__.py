@@ -54,6 +54,8 @@ _SIGS = {
     "dvbs2b200_version": (C.c_int, []),
     "dvbs2b200_last_error": (C.c_char_p, []),
     "dvbs2b200_device_count": (C.c_int, []),
+    "dvbs2b200_host_register": (C.c_int, [_P, C.c_size_t]),
+    "dvbs2b200_host_unregister": (C.c_int, [_P]),
     "dvbs2b200_num_tables": (C.c_int, []),
     "dvbs2b200_table_name": (C.c_char_p, [C.c_int]),
     "dvbs2b200_lookup": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(CodeInfo)]),
@@ -131,6 +133,15 @@ def lib():
 def _check(rc):
     if rc != 0:
         raise Dvbs2Error(rc, lib().dvbs2b200_last_error().decode())
+
+
+def host_register(array):
+    """Page-lock a numpy array the caller keeps across calls (dvbs2b200_host_register)."""
+    _check(lib().dvbs2b200_host_register(array.ctypes.data, array.nbytes))
+
+
+def host_unregister(array):
+    _check(lib().dvbs2b200_host_unregister(array.ctypes.data))
 
 
 def device_count():

@@ -83,6 +83,12 @@ typedef struct {
 int dvbs2b200_version(void);
 const char* dvbs2b200_last_error(void); /* thread-local, never NULL */
 int dvbs2b200_device_count(void);       /* >= 0, or DVBS2B200_ECUDA */
+/* Page-lock a host buffer the caller keeps across calls (a GNU Radio block's ring buffers live as long as the
+ * flowgraph: register them once in start(), unregister in stop()).  The host entry points then copy from / to it
+ * directly instead of staging through the handle's pinned ring (bench.py: e2e vs e2e_pageable).  Thin wrappers of
+ * cudaHostRegister(portable) / cudaHostUnregister; registering the same range twice is an error of the driver's. */
+int dvbs2b200_host_register(void* ptr, size_t bytes);
+int dvbs2b200_host_unregister(void* ptr);
 
 /* ---- code parameters (pure host functions, usable without a GPU) -------------------------- */
 int dvbs2b200_num_tables(void);

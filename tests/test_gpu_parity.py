@@ -301,3 +301,25 @@ def test_table_demapper_16apsk_32apsk(gpu, oracle):
         code.close()
     with pytest.raises(d.Dvbs2Error):
         d.Code(0, 1, d.C1_2).demap_table(np.zeros((64, 2), np.float32), np.zeros(6, np.int32), np.zeros((1, 10800, 2), np.float32), 1.0)
+
+
+def test_host_register_takes_the_direct_copy_path(gpu, oracle):
+    """A caller-owned pageable buffer page-locked in place (dvbs2b200_host_register) gives the same bytes as the
+    staged pageable path and as pinned memory; unregistering twice is an error, not a crash."""
+    d = gpu
+    from dvbs2rx_b200 import vectors
+    rate = d.RATE["C1_2"]
+    msg, cw, llr, info = vectors.make_llr_frames(S2, NORMAL, rate, 40, 2.0, seed=9)
+    code = d.Code(S2, NORMAL, rate)
+    want, tr0, co0 = code.fec_decode(llr=llr)            # pageable: staged through the pinned ring
+    buf = np.array(llr, copy=True)
+    d.host_register(buf)
+    try:
+        got, tr1, co1 = code.fec_decode(llr=buf)         # registered: copied from directly
+    finally:
+        d.host_unregister(buf)
+    assert np.array_equal(got, want) and np.array_equal(tr0, tr1) and np.array_equal(co0, co1)
+    assert np.array_equal(got, msg)
+    with pytest.raises(d.Dvbs2Error):
+        d.host_unregister(buf)
+    code.close()
