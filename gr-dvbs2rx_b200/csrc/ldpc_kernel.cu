@@ -372,7 +372,10 @@ __global__ void __launch_bounds__(kLdpcThreads) __maxnreg__(ldpc_regs(CNT_MAX, S
             if (!proven_bad) {
                 // bad(): any unsatisfied check.  A frame that is still bad shows it within a few layers, so the pass
                 // goes over the layers in chunks and stops at the first chunk with an unsatisfied check.
-                constexpr int kSyndromeChunk = 8;
+#ifndef DVBS2_SYNDROME_CHUNK
+#define DVBS2_SYNDROME_CHUNK 4
+#endif
+                constexpr int kSyndromeChunk = DVBS2_SYNDROME_CHUNK;
                 bad = 0;
 #pragma unroll 1
                 for (int i0 = 0; i0 < q && !bad; i0 += kSyndromeChunk) {
