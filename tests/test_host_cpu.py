@@ -99,6 +99,12 @@ def test_compute_calls_fail_loudly_without_a_gpu(built):
     with pytest.raises(d.Dvbs2Error) as e:
         d.Code(d.STANDARD_DVBS2, d.FECFRAME_NORMAL, d.C1_2)
     assert e.value.code == d.ECUDA and "no CPU fallback" in str(e.value)
+    # the other handle types and the page-locking helper fail the same way: an error code, no crash, no fallback
+    for make in (lambda: d.MixedCodes([(0, 1, d.C1_2), (0, 0, d.C2_3)]), lambda: d.MultiCode([0], 0, 1, d.C1_2),
+                 lambda: d.PlDescrambler(0, 0), lambda: d.host_register(np.zeros(4096, dtype=np.uint8))):
+        with pytest.raises(d.Dvbs2Error) as e:
+            make()
+        assert e.value.code == d.ECUDA
 
 
 def test_vector_generator_roundtrips_through_the_oracle(oracle):
