@@ -169,8 +169,9 @@ __global__ void __launch_bounds__(256) snr_kernel(const SnrLaunch p)
 // |y|^2 is common to every distance and cancels in the difference: the metric of point s is |s|^2 - 2 Re(y conj s),
 // two FMAs.  The 2 x BITS minima come from a halving tree: at the level of label bit b the metrics are split by
 // that bit (two minima) and folded pairwise over it for the remaining bits -- 82 min operations instead of 160
-// for 32 points, and the compiler fuses pairs of them into three-input FMNMX3.  A thread demaps four consecutive
-// symbols (two 128-bit loads) and stores one 32-bit word per bit row.
+// for 32 points, and the compiler fuses pairs of them into three-input FMNMX3.  A thread demaps two consecutive
+// symbols (one 128-bit load) and stores one 16-bit word per bit row.  About 170 instructions per 32APSK symbol, 105 of
+// them on the ALU pipe (FMNMX): that pipe, not HBM, is the bound.
 template <int BITS>
 __global__ void __launch_bounds__(256, 3) demap_table_kernel(const TableDemapLaunch p, const TableDemapConst t)
 {
