@@ -172,6 +172,11 @@ __global__ void __launch_bounds__(256) snr_kernel(const SnrLaunch p)
 // for 32 points, and the compiler fuses pairs of them into three-input FMNMX3.  A thread demaps two consecutive
 // symbols (one 128-bit load) and stores one 16-bit word per bit row.  About 170 instructions per 32APSK symbol, 105 of
 // them on the ALU pipe (FMNMX): that pipe, not HBM, is the bound.
+#ifndef DVBS2_TABLE_LOADS
+#define DVBS2_TABLE_LOADS 4
+#endif
+constexpr int kTableLoads = DVBS2_TABLE_LOADS;
+
 template <int BITS>
 __global__ void __launch_bounds__(256, 3) demap_table_kernel(const TableDemapLaunch p, const TableDemapConst t)
 {
@@ -185,38 +190,57 @@ __global__ void __launch_bounds__(256, 3) demap_table_kernel(const TableDemapLau
     // two consecutive symbols per thread (one 128-bit load), one 16-bit store per bit row: n_syms and the row offsets are
     // even for every DVB-S2 APSK frame (4050, 16200, 3240, 12960 symbols) -- checked by the host
     const int pairs = p.n_syms >> 1;
-    for (int pr = blockIdx.x * blockDim.x + threadIdx.x; pr < pairs; pr += gridDim.x * blockDim.x) {
-        const float4 y01 = __ldcs(in + pr);
-        uint32_t packed[BITS];
+    // kTableLoads 128-bit loads in flight per thread before the arithmetic starts: with one, a warp has 512 bytes under
+    // way for ~400 instructions of work and the SM cannot cover the DRAM latency (long-scoreboard stalls, 23 - 31 % of
+    // the HBM rate; four loads: 26 - 37 %, then the ALU pipe binds).  The symbol pairs are taken one after the other
+    // (unrolling them spills the 32 metrics of a symbol)
+    for (int pr0 = blockIdx.x * (kTableLoads * blockDim.x) + threadIdx.x; pr0 < pairs; pr0 += gridDim.x * kTableLoads * blockDim.x) {
+        float4 y[kTableLoads];
 #pragma unroll
-        for (int k = 0; k < BITS; ++k)
-            packed[k] = 0u;
-#pragma unroll 1 // one symbol at a time: 2^BITS live metrics
-        for (int u = 0; u < 2; ++u) {
-            const float yx = u == 0 ? y01.x : y01.z, yy = u == 0 ? y01.y : y01.w;
-            float v[NP];
-#pragma unroll
-            for (int s = 0; s < NP; ++s)
-                v[s] = fmaf(yx, t.a[s], fmaf(yy, t.b[s], t.c[s]));
-            // level lvl: label bit k = BITS - 1 - lvl is the LOW bit of the current index
-#pragma unroll
-            for (int lvl = 0; lvl < BITS; ++lvl) {
-                const int n = NP >> lvl, k = BITS - 1 - lvl;
-                float d0 = v[0], d1 = v[1];
-#pragma unroll
-                for (int i2 = 2; i2 < n; i2 += 2) {
-                    d0 = fminf(d0, v[i2]);
-                    d1 = fminf(d1, v[i2 + 1]);
-                }
-#pragma unroll
-                for (int i2 = 0; i2 < n; i2 += 2)
-                    v[i2 >> 1] = fminf(v[i2], v[i2 + 1]);
-                packed[k] |= convert_8i_sat(__fmul_rn(__fsub_rn(d1, d0), inv_n0)) << (8 * u);
-            }
+        for (int h = 0; h < kTableLoads; ++h) {
+            const int pr = pr0 + h * (int)blockDim.x;
+            y[h] = pr < pairs ? __ldcs(in + pr) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+#pragma unroll 1
+        for (int h = 0; h < kTableLoads; ++h) {
+            const int pr = pr0 + h * (int)blockDim.x;
+            if (pr >= pairs)
+                break;
+            float4 y01 = y[0];
 #pragma unroll
-        for (int k = 0; k < BITS; ++k)
-            *reinterpret_cast<uint16_t*>(out + t.row[k] + 2 * pr) = (uint16_t)packed[k];
+            for (int g = 1; g < kTableLoads; ++g)
+                y01 = h == g ? y[g] : y01;
+            uint32_t packed[BITS];
+#pragma unroll
+            for (int k = 0; k < BITS; ++k)
+                packed[k] = 0u;
+#pragma unroll 1 // one symbol at a time: 2^BITS live metrics
+            for (int u = 0; u < 2; ++u) {
+                const float yx = u == 0 ? y01.x : y01.z, yy = u == 0 ? y01.y : y01.w;
+                float v[NP];
+#pragma unroll
+                for (int s = 0; s < NP; ++s)
+                    v[s] = fmaf(yx, t.a[s], fmaf(yy, t.b[s], t.c[s]));
+                // level lvl: label bit k = BITS - 1 - lvl is the LOW bit of the current index
+#pragma unroll
+                for (int lvl = 0; lvl < BITS; ++lvl) {
+                    const int n = NP >> lvl, k = BITS - 1 - lvl;
+                    float d0 = v[0], d1 = v[1];
+#pragma unroll
+                    for (int i2 = 2; i2 < n; i2 += 2) {
+                        d0 = fminf(d0, v[i2]);
+                        d1 = fminf(d1, v[i2 + 1]);
+                    }
+#pragma unroll
+                    for (int i2 = 0; i2 < n; i2 += 2)
+                        v[i2 >> 1] = fminf(v[i2], v[i2 + 1]);
+                    packed[k] |= convert_8i_sat(__fmul_rn(__fsub_rn(d1, d0), inv_n0)) << (8 * u);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < BITS; ++k)
+                *reinterpret_cast<uint16_t*>(out + t.row[k] + 2 * pr) = (uint16_t)packed[k];
+        }
     }
 }
 
@@ -228,7 +252,7 @@ cudaError_t demap_table_launch(const TableDemapLaunch& p, const TableDemapConst&
         return cudaSuccess;
     if (p.n_syms % 2)
         return cudaErrorInvalidValue;
-    dim3 grid((p.n_syms / 2 + 255) / 256, p.frames);
+    dim3 grid((p.n_syms / 2 + 256 * kTableLoads - 1) / (256 * kTableLoads), p.frames);
     switch (p.bits) {
     case 1: demap_table_kernel<1><<<grid, 256, 0, stream>>>(p, t); break;
     case 2: demap_table_kernel<2><<<grid, 256, 0, stream>>>(p, t); break;
