@@ -106,38 +106,76 @@ __global__ void __launch_bounds__(256) demap_8psk_kernel(const DemapLaunch p)
 //      240-281): Es/N0 = sum |ref|^2 / sum |x - ref|^2 with the reference points taken from the sliced symbols
 //      (llr == null) or from the signs of the posterior LLRs.  Floating point sums: tolerance-checked, the
 //      reference's own summation order (VOLK) is unspecified.  HBM bound: 8 bytes per symbol (+ bits per symbol).
+// One symbol's contribution.  CONSTELLATION and HAS_LLR are compile-time: no branch per symbol.
+template <int CONSTELLATION, bool HAS_LLR>
+__device__ __forceinline__ void snr_symbol(const SnrLaunch& p, const int8_t* __restrict__ llr, int j, float xr, float xi, float& sp, float& np)
+{
+    const float a = 0.70710678118654752440f;
+    const float rot_re = (float)0.92387953251128675613, rot_im = (float)-0.38268343236508977173;
+    float sr, si;
+    if (CONSTELLATION == 0) {
+        const bool pr = HAS_LLR ? llr[2 * j] >= 0 : xr >= 0.f, pi = HAS_LLR ? llr[2 * j + 1] >= 0 : xi >= 0.f;
+        sr = pr ? a : -a;
+        si = pi ? a : -a;
+    } else {
+        bool b0, b1, b2; // true = the bit's LLR is negative
+        if (HAS_LLR) {
+            b0 = llr[p.row0 + j] < 0, b1 = llr[p.row1 + j] < 0, b2 = llr[p.row2 + j] < 0;
+        } else { // lib/psk.hh:135-141
+            const float re = __fsub_rn(__fmul_rn(xr, rot_re), __fmul_rn(xi, rot_im));
+            const float im = __fadd_rn(__fmul_rn(xr, rot_im), __fmul_rn(xi, rot_re));
+            b1 = re < 0.f, b2 = im < 0.f, b0 = fabsf(re) < fabsf(im);
+        }
+        // lib/psk.hh:114-121,152-157: point 4 b0 + 2 b1 + b2 of { (a,a), (1,0), (-1,0), (-a,-a), (0,1), (a,-a), (-a,a), (0,-1) },
+        // by selects (an indexed table would live in local memory)
+        sr = b0 ? (b1 ? (b2 ? 0.f : -a) : (b2 ? a : 0.f)) : (b1 ? (b2 ? -a : -1.f) : (b2 ? 1.f : a));
+        si = b0 ? (b1 ? (b2 ? -1.f : a) : (b2 ? -a : 1.f)) : (b1 ? (b2 ? -a : 0.f) : (b2 ? 0.f : a));
+    }
+    const float er = xr - sr, ei = xi - si;
+    sp += sr * sr + si * si;
+    np += er * er + ei * ei;
+}
+
+// Two symbols per 128-bit load, kSnrLoads loads in flight per thread (a frame is 64.8 - 259 KB of symbols: with one
+// 8-byte load per thread and iteration the CTA had too little under way to cover the DRAM latency).
+constexpr int kSnrLoads = 4;
+
+template <int CONSTELLATION, bool HAS_LLR>
+__device__ __forceinline__ void snr_frame(const SnrLaunch& p, int frame, int tid, float& sp, float& np)
+{
+    const float4* __restrict__ in = reinterpret_cast<const float4*>(p.iq + (size_t)frame * p.n_syms * 2);
+    const int8_t* __restrict__ llr = HAS_LLR ? p.llr + (size_t)frame * p.n_syms * (CONSTELLATION == 0 ? 2 : 3) : nullptr;
+    const int pairs = p.n_syms >> 1; // n_syms is even for every frame size (checked by the host)
+    for (int j0 = tid; j0 < pairs; j0 += 256 * kSnrLoads) {
+        float4 x[kSnrLoads];
+#pragma unroll
+        for (int h = 0; h < kSnrLoads; ++h)
+            x[h] = j0 + 256 * h < pairs ? __ldcs(in + j0 + 256 * h) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int h = 0; h < kSnrLoads; ++h) {
+            const int j = 2 * (j0 + 256 * h);
+            if (j0 + 256 * h < pairs) {
+                snr_symbol<CONSTELLATION, HAS_LLR>(p, llr, j, x[h].x, x[h].y, sp, np);
+                snr_symbol<CONSTELLATION, HAS_LLR>(p, llr, j + 1, x[h].z, x[h].w, sp, np);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) snr_kernel(const SnrLaunch p)
 {
     const int frame = blockIdx.x, tid = threadIdx.x;
-    const float2* __restrict__ in = reinterpret_cast<const float2*>(p.iq + (size_t)frame * p.n_syms * 2);
-    const int8_t* __restrict__ llr = p.llr ? p.llr + (size_t)frame * p.n_syms * (p.constellation == 0 ? 2 : 3) : nullptr;
-    const float a = 0.70710678118654752440f;
-    const float rot_re = (float)0.92387953251128675613, rot_im = (float)-0.38268343236508977173;
     float sp = 0.f, np = 0.f;
-    for (int j = tid; j < p.n_syms; j += 256) {
-        const float2 x = __ldcs(in + j);
-        float sr, si;
-        if (p.constellation == 0) {
-            const bool pr = llr ? llr[2 * j] >= 0 : x.x >= 0.f, pi = llr ? llr[2 * j + 1] >= 0 : x.y >= 0.f;
-            sr = pr ? a : -a;
-            si = pi ? a : -a;
-        } else {
-            bool b0, b1, b2; // true = the bit's LLR is negative
-            if (llr) {
-                b0 = llr[p.row0 + j] < 0, b1 = llr[p.row1 + j] < 0, b2 = llr[p.row2 + j] < 0;
-            } else { // lib/psk.hh:135-141
-                const float re = __fsub_rn(__fmul_rn(x.x, rot_re), __fmul_rn(x.y, rot_im));
-                const float im = __fadd_rn(__fmul_rn(x.x, rot_im), __fmul_rn(x.y, rot_re));
-                b1 = re < 0.f, b2 = im < 0.f, b0 = fabsf(re) < fabsf(im);
-            }
-            // lib/psk.hh:114-121,152-157: index = 4 b0 + 2 b1 + b2
-            const int idx = (b0 ? 4 : 0) | (b1 ? 2 : 0) | (b2 ? 1 : 0);
-            const float tr[8] = { a, 1.f, -1.f, -a, 0.f, a, -a, 0.f }, ti[8] = { a, 0.f, 0.f, -a, 1.f, -a, a, -1.f };
-            sr = tr[idx], si = ti[idx];
-        }
-        const float er = x.x - sr, ei = x.y - si;
-        sp += sr * sr + si * si;
-        np += er * er + ei * ei;
+    if (p.constellation == 0) {
+        if (p.llr)
+            snr_frame<0, true>(p, frame, tid, sp, np);
+        else
+            snr_frame<0, false>(p, frame, tid, sp, np);
+    } else {
+        if (p.llr)
+            snr_frame<4, true>(p, frame, tid, sp, np);
+        else
+            snr_frame<4, false>(p, frame, tid, sp, np);
     }
     __shared__ float s_sp[8], s_np[8];
 #pragma unroll
@@ -268,6 +306,8 @@ cudaError_t snr_launch(const SnrLaunch& p, cudaStream_t stream)
 {
     if (p.frames <= 0)
         return cudaSuccess;
+    if (p.n_syms % 2)
+        return cudaErrorInvalidValue;
     snr_kernel<<<p.frames, 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
