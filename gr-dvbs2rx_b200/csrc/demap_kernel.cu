@@ -19,24 +19,17 @@ namespace dvbs2b200 {
 
 namespace {
 
-// volk_32f_s32f_convert_8i_generic: clamp first, then rintf (round half to even)
-__device__ __forceinline__ int convert_8i(float r)
-{
-    if (r > 127.0f)
-        return 127;
-    if (r < -128.0f)
-        return -128;
-    return __float2int_rn(r);
-}
-
-// the same in one instruction: round to nearest even, then saturate to int8 (identical for every finite input:
-// anything above 127 or below -128 ends at the rail either way); the low byte of the result is the int8
+// volk_32f_s32f_convert_8i_generic: clamp to [-128, 127] first, then rintf (round half to even) ...
+// ... which is one instruction: round to nearest even, then saturate to int8 (identical for every input: anything
+// above 127 or below -128 ends at the rail either way, NaN gives 0 both ways); the low byte of the result is the int8
 __device__ __forceinline__ uint32_t convert_8i_sat(float r)
 {
     int v;
     asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(v) : "f"(r));
     return (uint32_t)v & 0xffu;
 }
+
+constexpr int kQpskLoads = 4;
 
 __global__ void __launch_bounds__(256) demap_qpsk_kernel(const DemapLaunch p)
 {
@@ -45,13 +38,23 @@ __global__ void __launch_bounds__(256) demap_qpsk_kernel(const DemapLaunch p)
     const float scalar = (float)(2.0 * 1.41421356237309504880 / (double)p.n0[frame]);
     const float4* __restrict__ in = reinterpret_cast<const float4*>(p.iq + (size_t)frame * p.n_syms * 2);
     uint32_t* __restrict__ out = reinterpret_cast<uint32_t*>(p.llr + (size_t)frame * p.n_syms * 2);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_f4; i += gridDim.x * blockDim.x) {
-        const float4 v = __ldcs(in + i); // streamed once
-        const uint32_t b0 = (uint32_t)convert_8i(__fmul_rn(v.x, scalar)) & 0xffu;
-        const uint32_t b1 = (uint32_t)convert_8i(__fmul_rn(v.y, scalar)) & 0xffu;
-        const uint32_t b2 = (uint32_t)convert_8i(__fmul_rn(v.z, scalar)) & 0xffu;
-        const uint32_t b3 = (uint32_t)convert_8i(__fmul_rn(v.w, scalar)) & 0xffu;
-        out[i] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+    // kQpskLoads 128-bit loads in flight per thread, streamed once
+    for (int i0 = blockIdx.x * (kQpskLoads * blockDim.x) + threadIdx.x; i0 < n_f4; i0 += gridDim.x * kQpskLoads * blockDim.x) {
+        float4 v[kQpskLoads];
+#pragma unroll
+        for (int h = 0; h < kQpskLoads; ++h)
+            v[h] = i0 + h * (int)blockDim.x < n_f4 ? __ldcs(in + i0 + h * (int)blockDim.x) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int h = 0; h < kQpskLoads; ++h) {
+            const int i = i0 + h * (int)blockDim.x;
+            if (i < n_f4) {
+                const uint32_t b0 = convert_8i_sat(__fmul_rn(v[h].x, scalar));
+                const uint32_t b1 = convert_8i_sat(__fmul_rn(v[h].y, scalar));
+                const uint32_t b2 = convert_8i_sat(__fmul_rn(v[h].z, scalar));
+                const uint32_t b3 = convert_8i_sat(__fmul_rn(v[h].w, scalar));
+                __stcs(out + i, b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
+            }
+        }
     }
 }
 
@@ -62,6 +65,8 @@ __device__ __forceinline__ uint32_t quantize8(float scale, float value)
     r = fminf(fmaxf(r, -128.0f), 127.0f);
     return (uint32_t)((int)r) & 0xffu;
 }
+
+constexpr int kPskGroups = 2;
 
 __global__ void __launch_bounds__(256) demap_8psk_kernel(const DemapLaunch p)
 {
@@ -78,27 +83,41 @@ __global__ void __launch_bounds__(256) demap_8psk_kernel(const DemapLaunch p)
     uint32_t* __restrict__ c0 = reinterpret_cast<uint32_t*>(out + p.row0);
     uint32_t* __restrict__ c1 = reinterpret_cast<uint32_t*>(out + p.row1);
     uint32_t* __restrict__ c2 = reinterpret_cast<uint32_t*>(out + p.row2);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
-        uint32_t w0 = 0, w1 = 0, w2 = 0;
+    // kPskGroups groups of 4 symbols per thread: all their 128-bit loads are issued before the arithmetic starts
+    for (int i0 = blockIdx.x * (kPskGroups * blockDim.x) + threadIdx.x; i0 < n4; i0 += gridDim.x * kPskGroups * blockDim.x) {
+        float4 v[kPskGroups][2];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const float4 v = __ldcs(in + 2 * i + h);
-            const float a[2] = { v.x, v.z }, b[2] = { v.y, v.w };
+        for (int g = 0; g < kPskGroups; ++g) {
+            const int i = i0 + g * (int)blockDim.x;
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                // std::complex<float> c *= rot: (a*c - b*d) + (a*d + b*c) i, unfused
-                const float re = __fsub_rn(__fmul_rn(a[s], rot_re), __fmul_rn(b[s], rot_im));
-                const float im = __fadd_rn(__fmul_rn(a[s], rot_im), __fmul_rn(b[s], rot_re));
-                const float m0 = __fmul_rn(rcp_sqrt_2, __fsub_rn(fabsf(re), fabsf(im)));
-                const int sh = 8 * (2 * h + s);
-                w0 |= quantize8(scale, m0) << sh;
-                w1 |= quantize8(scale, re) << sh;
-                w2 |= quantize8(scale, im) << sh;
-            }
+            for (int h = 0; h < 2; ++h)
+                v[g][h] = i < n4 ? __ldcs(in + 2 * i + h) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        c0[i] = w0;
-        c1[i] = w1;
-        c2[i] = w2;
+#pragma unroll
+        for (int g = 0; g < kPskGroups; ++g) {
+            const int i = i0 + g * (int)blockDim.x;
+            if (i >= n4)
+                break;
+            uint32_t w0 = 0, w1 = 0, w2 = 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float a[2] = { v[g][h].x, v[g][h].z }, b[2] = { v[g][h].y, v[g][h].w };
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    // std::complex<float> c *= rot: (a*c - b*d) + (a*d + b*c) i, unfused
+                    const float re = __fsub_rn(__fmul_rn(a[s], rot_re), __fmul_rn(b[s], rot_im));
+                    const float im = __fadd_rn(__fmul_rn(a[s], rot_im), __fmul_rn(b[s], rot_re));
+                    const float m0 = __fmul_rn(rcp_sqrt_2, __fsub_rn(fabsf(re), fabsf(im)));
+                    const int sh = 8 * (2 * h + s);
+                    w0 |= quantize8(scale, m0) << sh;
+                    w1 |= quantize8(scale, re) << sh;
+                    w2 |= quantize8(scale, im) << sh;
+                }
+            }
+            __stcs(c0 + i, w0);
+            __stcs(c1 + i, w1);
+            __stcs(c2 + i, w2);
+        }
     }
 }
 
@@ -319,11 +338,11 @@ cudaError_t demap_launch(const DemapLaunch& p, cudaStream_t stream)
     const int threads = 256;
     if (p.constellation == 0) {
         const int work = p.n_syms / 2;
-        dim3 grid((work + threads * 2 - 1) / (threads * 2), p.frames);
+        dim3 grid((work + threads * kQpskLoads - 1) / (threads * kQpskLoads), p.frames);
         demap_qpsk_kernel<<<grid, threads, 0, stream>>>(p);
     } else if (p.constellation == 4) {
         const int work = p.n_syms / 4;
-        dim3 grid((work + threads - 1) / threads, p.frames);
+        dim3 grid((work + threads * kPskGroups - 1) / (threads * kPskGroups), p.frames);
         demap_8psk_kernel<<<grid, threads, 0, stream>>>(p);
     } else {
         return cudaErrorInvalidValue;
