@@ -121,7 +121,7 @@ struct dvbs2b200_code {
     int ldpc_ctas = 0;      // resident LDPC CTAs per SM
     uint64_t launches = 0;
     // staging for the host-pointer entry points
-    DevBuf d_in, d_mid, d_out, d_post, d_i32a, d_i32b, d_n0, d_llr, d_sync, d_scratch, d_flag, d_prof;
+    DevBuf d_in, d_mid, d_out, d_post, d_i32a, d_i32b, d_n0, d_llr, d_sync, d_scratch, d_flag, d_prof, d_next;
     // BB layer: descrambling sequence, deheader stream state, per-call scratch, TS output staging
     DevBuf d_prbs, d_bbstate, d_bbrec, d_bbplan, d_ts;
     DevBuf d_points; // table-driven demapper: constellation [32][2] floats + row offsets [5] ints
@@ -351,6 +351,14 @@ int ldpc_dev(dvbs2b200_code* h, const int8_t* d_llr, int frames, int max_trials,
             return rc;
         CU(cudaMemsetAsync(h->d_sync.p, 0, words * sizeof(unsigned), stream));
         p.gsync = (unsigned*)h->d_sync.p;
+    }
+    else {
+        // frames converge after different numbers of iterations: hand them out dynamically
+        int rc = h->d_next.ensure(16);
+        if (rc)
+            return rc;
+        CU(cudaMemsetAsync(h->d_next.p, 0, 4, stream));
+        p.next_frame = (unsigned int*)h->d_next.p;
     }
 #ifdef DVBS2_PHASE_PROFILE
     const char* prof_path = getenv("DVBS2B200_PHASE_PROFILE"); // diagnostics build: per-CTA cycles per phase
@@ -786,7 +794,7 @@ void dvbs2b200_code_destroy(dvbs2b200_code* h)
     for (cudaStream_t st : { h->stream, h->s_in, h->s_out })
         if (st)
             cudaStreamSynchronize(st);
-    for (DevBuf* b : { &h->d_in, &h->d_mid, &h->d_out, &h->d_post, &h->d_i32a, &h->d_i32b, &h->d_n0, &h->d_llr, &h->d_sync, &h->d_scratch, &h->d_flag, &h->d_prof,
+    for (DevBuf* b : { &h->d_in, &h->d_mid, &h->d_out, &h->d_post, &h->d_i32a, &h->d_i32b, &h->d_n0, &h->d_llr, &h->d_sync, &h->d_scratch, &h->d_flag, &h->d_prof, &h->d_next,
                        &h->d_prbs, &h->d_bbstate, &h->d_bbrec, &h->d_bbplan, &h->d_ts, &h->d_points, &h->d_err })
         b->release();
     for (HostBuf* b : { &h->h_ring, &h->h_out, &h->h_cnt })

@@ -30,6 +30,9 @@ struct LdpcLaunch {
     int max_trials;
     int group;           // 0 per-frame termination, else frames per coupled group
     unsigned int* gsync; // [frames/group][max_trials + 2], zeroed (group mode only)
+    // per-frame termination: frames beyond the first wave are handed out through this counter (zeroed before the launch)
+    // instead of by stride, so a CTA whose frames converge early takes more of them (null: by stride)
+    unsigned int* next_frame;
     uint8_t* hard;       // [frames][out_bytes] or null
     int out_bytes;
     int8_t* llr_post;     // [frames][N] or null, 4-byte aligned

@@ -316,7 +316,9 @@ __global__ void __launch_bounds__(kLdpcThreads) __maxnreg__(ldpc_regs(CNT_MAX, S
 #define COUNT(slot) ((void)0)
 #define COUNTN(slot, n) ((void)0)
 #endif
-    for (int f = blockIdx.x; f < p.frames; f += gridDim.x) {
+    __shared__ int s_next_frame;
+    int f = blockIdx.x;
+    while (f < p.frames) {
         // ---- streaming input: wait until the host->device copy of this frame's chunk has landed ----
         if (p.ready) {
             if (tid == 0) {
@@ -552,6 +554,14 @@ __global__ void __launch_bounds__(kLdpcThreads) __maxnreg__(ldpc_regs(CNT_MAX, S
         }
         __syncthreads(); // L is reused by the next frame
         LAP(7);
+        if (p.next_frame) { // next frame: whichever is next in the batch (frames take different numbers of iterations)
+            if (tid == 0)
+                s_next_frame = (int)gridDim.x + (int)atomicAdd(p.next_frame, 1u);
+            __syncthreads();
+            f = s_next_frame;
+        } else {
+            f += gridDim.x;
+        }
     }
 #ifdef DVBS2_PHASE_PROFILE
     if (p.prof && tid == 0) {
